@@ -1,0 +1,187 @@
+// context.cu -- context lifecycle, memory helpers, timers and error reporting of the C ABI.
+#include "internal.h"
+
+#include <cstring>
+
+namespace clumpy {
+
+static thread_local std::string g_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+// Order-preserving float <-> uint32 encoding so that atomicMin/atomicMax on unsigned ints reduce
+// floats.  NaNs never reach the atomics (the kernels only submit values that won a `<` test).
+__global__ void minmax_reset_kernel(uint32_t* mm) {
+    mm[0] = 0xFFFFFFFFu; // +max
+    mm[1] = 0u;          // lowest
+}
+
+static float decode_ordered(uint32_t u) {
+    uint32_t bits = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+
+int minmax_reset(clumpy_cuda_ctx* ctx) {
+    minmax_reset_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_minmax);
+    CK_LAUNCH(ctx);
+    return CLUMPY_OK;
+}
+
+int minmax_fetch(clumpy_cuda_ctx* ctx, float* minval, float* maxval) {
+    CK(cudaMemcpyAsync(ctx->h_minmax, ctx->d_minmax, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // An untouched slot decodes to the reference's initial numeric_limits max / lowest.
+    float lo = ctx->h_minmax[0] == 0xFFFFFFFFu ? 3.402823466e+38f : decode_ordered(ctx->h_minmax[0]);
+    float hi = ctx->h_minmax[1] == 0u ? -3.402823466e+38f : decode_ordered(ctx->h_minmax[1]);
+    if (minval) *minval = lo;
+    if (maxval) *maxval = hi;
+    return CLUMPY_OK;
+}
+
+} // namespace clumpy
+
+using namespace clumpy;
+
+CLUMPY_API const char* clumpy_cuda_last_error(void) { return g_error.c_str(); }
+
+CLUMPY_API int clumpy_cuda_device_count(int* count) {
+    REQUIRE(count, "count is NULL");
+    *count = 0;
+    CK(cudaGetDeviceCount(count));
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_create(int device, void* stream, clumpy_cuda_ctx** out) {
+    REQUIRE(out, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) {
+        set_error("no CUDA device is visible; libclumpy_cuda has no CPU fallback");
+        return CLUMPY_ERR_CUDA;
+    }
+    REQUIRE(device >= 0 && device < ndev, "device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                  prop.major, prop.minor);
+        return CLUMPY_ERR_CUDA;
+    }
+    clumpy_cuda_ctx* ctx = new (std::nothrow) clumpy_cuda_ctx();
+    if (!ctx) { set_error("out of host memory"); return CLUMPY_ERR_NOMEM; }
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ctx->t0));
+    CK(cudaEventCreate(&ctx->t1));
+    CK(cudaMalloc(&ctx->d_minmax, 8));
+    CK(cudaMallocHost(&ctx->h_minmax, 8));
+    *out = ctx;
+    return CLUMPY_OK;
+}
+
+CLUMPY_API void clumpy_cuda_destroy(clumpy_cuda_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaEventDestroy(ctx->t0);
+    cudaEventDestroy(ctx->t1);
+    cudaFree(ctx->d_minmax);
+    cudaFreeHost(ctx->h_minmax);
+    delete ctx;
+}
+
+CLUMPY_API int clumpy_cuda_sync(clumpy_cuda_ctx* ctx) {
+    REQUIRE(ctx, "ctx is NULL");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    return CLUMPY_OK;
+}
+
+CLUMPY_API void* clumpy_cuda_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        set_error("cudaMallocHost(%zu) failed", bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+CLUMPY_API void clumpy_cuda_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+CLUMPY_API int clumpy_cuda_dev_alloc(clumpy_cuda_ctx* ctx, size_t bytes, void** dptr) {
+    REQUIRE(ctx && dptr, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMalloc(dptr, bytes ? bytes : 1));
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_dev_free(clumpy_cuda_ctx* ctx, void* dptr) {
+    REQUIRE(ctx, "ctx is NULL");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(dptr));
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_memcpy_h2d(clumpy_cuda_ctx* ctx, void* dst_dev, const void* src_host,
+                                      size_t bytes) {
+    REQUIRE(ctx && (bytes == 0 || (dst_dev && src_host)), "null argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_memcpy_d2h(clumpy_cuda_ctx* ctx, void* dst_host, const void* src_dev,
+                                      size_t bytes) {
+    REQUIRE(ctx && (bytes == 0 || (dst_host && src_dev)), "null argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_timer_start(clumpy_cuda_ctx* ctx) {
+    REQUIRE(ctx, "ctx is NULL");
+    CK(cudaEventRecord(ctx->t0, ctx->stream));
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_timer_stop(clumpy_cuda_ctx* ctx, float* elapsed_ms) {
+    REQUIRE(ctx && elapsed_ms, "null argument");
+    CK(cudaEventRecord(ctx->t1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->t1));
+    CK(cudaEventElapsedTime(elapsed_ms, ctx->t0, ctx->t1));
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_launch_count(clumpy_cuda_ctx* ctx, uint64_t* launches) {
+    REQUIRE(ctx && launches, "null argument");
+    *launches = ctx->launches;
+    return CLUMPY_OK;
+}

@@ -1,0 +1,174 @@
+/*
+ * clumpy_cuda.h -- C ABI of libclumpy_cuda.so, the B200 (sm_100a) implementation of clumpy's
+ * point-advection hot path:  generate_simplex -> curl_2d -> advect_points (+ splat_points).
+ *
+ * This is the drop-in boundary.  A clumpy command's `exec` (clumpy_command.hh:8-29) keeps its
+ * argument parsing, validation messages and .npy I/O on the host and calls ONE of the entry
+ * points below instead of its CPU loop.  Each entry point names the reference loop it replaces
+ * (paths relative to the clumpy source root).  See INTEGRATION.md for the binding a maintainer
+ * would add on the reference side.
+ *
+ * Conventions
+ *   - plain C types only; the caller owns every host pointer, the library owns device memory;
+ *   - every function returns CLUMPY_OK (0) or a CLUMPY_ERR_* code and never throws;
+ *     clumpy_cuda_last_error() returns the message of the calling thread's last failure;
+ *   - there is NO CPU fallback: without a usable CUDA device clumpy_cuda_create fails;
+ *   - `*_dev` variants take DEVICE pointers (memory resident in HBM, e.g. from
+ *     clumpy_cuda_dev_alloc) and enqueue work on the context's stream without synchronising
+ *     unless a host result (min/max) is requested;
+ *   - images are row-major (H, W[, 2]); points are (N, 2) float32 = (x, y) pairs;
+ *   - host buffers may be pageable or pinned (clumpy_cuda_host_alloc); pinned ones make the
+ *     copies asynchronous and run at PCIe speed.
+ */
+#ifndef CLUMPY_CUDA_H
+#define CLUMPY_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLUMPY_OK 0
+#define CLUMPY_ERR_INVALID 1 /* bad argument (even kernel size, null pointer, zero dims ...) */
+#define CLUMPY_ERR_CUDA 2    /* a CUDA runtime call or kernel failed                        */
+#define CLUMPY_ERR_NOMEM 3   /* host or device allocation failed                            */
+#define CLUMPY_ERR_STATE 4   /* call made in the wrong order (e.g. step after the last frame) */
+
+#define CLUMPY_MAX_KERNEL_SIZE 31 /* largest odd splat kernel the device path accepts */
+
+typedef struct clumpy_cuda_ctx clumpy_cuda_ctx; /* one device + its streams and scratch */
+typedef struct clumpy_advect clumpy_advect;     /* device-resident state of one advect_points run */
+
+/* ---- library / context ---------------------------------------------------------------- */
+
+const char* clumpy_cuda_last_error(void);
+int clumpy_cuda_device_count(int* count);
+
+/* `stream` is a cudaStream_t to run on (e.g. the caller's current stream so that the caller's
+ * CUDA events bracket the work), or NULL for a stream owned by the context. */
+int clumpy_cuda_create(int device, void* stream, clumpy_cuda_ctx** out);
+void clumpy_cuda_destroy(clumpy_cuda_ctx* ctx);
+int clumpy_cuda_sync(clumpy_cuda_ctx* ctx);
+
+void* clumpy_cuda_host_alloc(size_t bytes); /* pinned host memory, NULL on failure */
+void clumpy_cuda_host_free(void* p);
+int clumpy_cuda_dev_alloc(clumpy_cuda_ctx* ctx, size_t bytes, void** dptr);
+int clumpy_cuda_dev_free(clumpy_cuda_ctx* ctx, void* dptr);
+int clumpy_cuda_memcpy_h2d(clumpy_cuda_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int clumpy_cuda_memcpy_d2h(clumpy_cuda_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+/* Device-side stopwatch on the context's stream (CUDA events). */
+int clumpy_cuda_timer_start(clumpy_cuda_ctx* ctx);
+int clumpy_cuda_timer_stop(clumpy_cuda_ctx* ctx, float* elapsed_ms); /* synchronises */
+
+/* Number of kernels this library has launched on `ctx` since creation. */
+int clumpy_cuda_launch_count(clumpy_cuda_ctx* ctx, uint64_t* launches);
+
+/* ---- generate_simplex ------------------------------------------------------------------ */
+
+/* Host helper: the 256-entry permutation of commands/generate_simplex.cc:241-280. */
+int clumpy_cuda_simplex_perm(int64_t seed, int16_t* perm256);
+
+/* Replaces the per-pixel loop of commands/generate_simplex.cc:59-82 (which calls
+ * open_simplex_noise2, :298-417).  out_host is (height, width) float32.  minval/maxval receive
+ * the "Noise range" the command prints (:78-82); either may be NULL. */
+int clumpy_cuda_generate_simplex(clumpy_cuda_ctx* ctx, uint32_t width, uint32_t height,
+                                 double amplitude, double frequency, int64_t seed,
+                                 float* out_host, float* minval, float* maxval);
+
+/* Row band [row0, row0+nrows) of the (height, width) image into out_dev (nrows x width floats).
+ * Bands are independent, which is how the field is sharded across GPUs. */
+int clumpy_cuda_generate_simplex_dev(clumpy_cuda_ctx* ctx, uint32_t width, uint32_t height,
+                                     uint32_t row0, uint32_t nrows, double amplitude,
+                                     double frequency, int64_t seed, float* out_dev,
+                                     float* minval, float* maxval);
+
+/* ---- curl_2d --------------------------------------------------------------------------- */
+
+/* Replaces the loop of commands/curl_2d.cc:57-71.  src_host (height, width) float32 ->
+ * dst_host (height, width, 2) float32 with texel = (dpdy, dpdx).  minval/maxval follow the
+ * reference's printed "Curl range" including its quirk (:64-65); either may be NULL. */
+int clumpy_cuda_curl_2d(clumpy_cuda_ctx* ctx, const float* src_host, uint32_t width,
+                        uint32_t height, float* dst_host, float* minval, float* maxval);
+
+/* A band of `nrows` rows starting at src_dev.  next_row_dev points at the row below the band
+ * (the one-row halo owned by the next band / next GPU) or is NULL when the band ends at the
+ * bottom edge of the image, where the reference clamps (:60). */
+int clumpy_cuda_curl_2d_dev(clumpy_cuda_ctx* ctx, const float* src_dev, uint32_t width,
+                            uint32_t nrows, const float* next_row_dev, float* dst_dev,
+                            float* minval, float* maxval);
+
+/* ---- splat_points ---------------------------------------------------------------------- */
+
+/* Replaces splat_points() (commands/splat_points.cc:108-116): marks the texel under each point
+ * with 255.  img_host (height, width) u8 is read, updated and written back. */
+int clumpy_cuda_splat_points(clumpy_cuda_ctx* ctx, const float* pts_host, uint32_t npts,
+                             uint32_t width, uint32_t height, uint8_t* img_host);
+
+/* Replaces splat_disks() (commands/splat_points.cc:118-161): src-over blend of a k x k smoothstep
+ * sprite of opacity `alpha` at every point into the u8 image.  wrapx is the reference's
+ * `advect_wrapx` global (:20).  Even kernel sizes return CLUMPY_ERR_INVALID (the reference
+ * prints "Kernel size must be an odd integer." and exits 1, :122-125). */
+int clumpy_cuda_splat_disks(clumpy_cuda_ctx* ctx, const float* pts_host, uint32_t npts,
+                            uint32_t width, uint32_t height, uint8_t* img_host, float alpha,
+                            int kernel_size, int wrapx);
+
+/* ---- advect_points --------------------------------------------------------------------- */
+
+/* Host helper: the per-point reset offsets of commands/advect_points.cc:127-135
+ * (std::mt19937 seeded with 0 + std::uniform_int_distribution<>(0, nframes-1), libstdc++). */
+int clumpy_cuda_age_offsets(uint32_t nframes, uint32_t npts, uint32_t* out);
+
+/* Set-up of commands/advect_points.cc:83-135: uploads the points (npts, 2) and the velocity
+ * field (height, width, 2), allocates the u8 framebuffer (zeroed) and the splat accumulator.
+ * `decay` is the non-negative decay; `wrapx` != 0 is what the command derives from a negative
+ * decay argument (:78-81).  age_offset may be NULL, in which case clumpy_cuda_age_offsets is
+ * used.  nframes is the number of RECORDED frames; the run has 2*nframes simulation frames. */
+int clumpy_cuda_advect_begin(clumpy_cuda_ctx* ctx, const float* pts_host, uint32_t npts,
+                             const float* vel_host, uint32_t width, uint32_t height,
+                             float step_size, int kernel_size, float decay, int wrapx,
+                             uint32_t nframes, const uint32_t* age_offset, clumpy_advect** out);
+
+/* Advances `count` simulation frames (commands/advect_points.cc:139-176 without the file write):
+ * Euler step + reset of every point, u8 decay, splat.  Asynchronous; no host copies. */
+int clumpy_cuda_advect_step(clumpy_advect* adv, uint32_t count);
+
+/* Like clumpy_cuda_advect_step, but brackets every kernel with CUDA events on the context's stream
+ * and returns the mean device time per frame (ms) of the advect+count kernel, the composite kernel
+ * and the counter clear.  Synchronises.  Used by bench.py for the roofline of the dominant kernel. */
+int clumpy_cuda_advect_profile(clumpy_advect* adv, uint32_t count, float* advect_ms,
+                               float* composite_ms, float* clear_ms);
+
+/* Number of simulation frames done so far; frames [nframes, 2*nframes) are the recorded ones. */
+int clumpy_cuda_advect_simframe(clumpy_advect* adv, uint32_t* simframe);
+
+/* Enqueues a device->host copy of the current framebuffer (height*width u8) on the context's
+ * copy stream, ordered after the steps issued so far; later steps do not wait for it unless they
+ * would overwrite the buffer being copied.  dst_host should be pinned for the copy to overlap. */
+int clumpy_cuda_advect_frame_async(clumpy_advect* adv, uint8_t* dst_host);
+int clumpy_cuda_advect_wait_frames(clumpy_advect* adv);
+
+/* Diagnostics for parity tests (the reference CLI never outputs trajectories): current positions
+ * in the caller's original point order, and the current framebuffer.  Both synchronise. */
+int clumpy_cuda_advect_read_points(clumpy_advect* adv, float* out_host);
+int clumpy_cuda_advect_read_image(clumpy_advect* adv, uint8_t* out_host);
+
+int clumpy_cuda_advect_end(clumpy_advect* adv);
+
+/* The whole command (commands/advect_points.cc:137-179): 2*nframes simulation frames; each of the
+ * last nframes framebuffers is copied to pinned host memory on a side stream and handed to
+ * `on_frame(user, animframe, pixels)` in order while the GPU keeps simulating.  A non-zero return
+ * from the callback aborts the run with CLUMPY_ERR_STATE. */
+typedef int (*clumpy_frame_fn)(void* user, uint32_t animframe, const uint8_t* pixels);
+int clumpy_cuda_advect_points(clumpy_cuda_ctx* ctx, const float* pts_host, uint32_t npts,
+                              const float* vel_host, uint32_t width, uint32_t height,
+                              float step_size, int kernel_size, float decay, int wrapx,
+                              uint32_t nframes, const uint32_t* age_offset,
+                              clumpy_frame_fn on_frame, void* user);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLUMPY_CUDA_H */

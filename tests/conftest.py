@@ -1,0 +1,51 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    """Outputs of the compiled reference (tests/golden/make_golden.py)."""
+    with open(os.path.join(GOLDEN, "golden.json")) as f:
+        meta = json.load(f)
+    return {
+        "meta": meta,
+        "fields": dict(np.load(os.path.join(GOLDEN, "fields.npz"))),
+        "advect": dict(np.load(os.path.join(GOLDEN, "advect_small.npz"))),
+        "splat": dict(np.load(os.path.join(GOLDEN, "splat_small.npz"))),
+        "c1_pts": np.load(os.path.join(GOLDEN, "c1_pts.npy")),
+    }
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    import oracle
+    oracle.lib()  # builds liboracle.so on first use
+    return oracle
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    """A libclumpy_cuda context on cuda:0.  No fallback: errors propagate."""
+    import clumpy_b200
+    c = clumpy_b200.Context(0)
+    yield c
+    c.close()
+
+
+def frame_agreement(a, b):
+    """(fraction of pixels within 1 LSB, max abs difference) between two u8 images."""
+    d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+    return float(np.mean(d <= 1)), int(d.max()) if d.size else 0

@@ -1,0 +1,270 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (clumpy_b200 -> libclumpy_cuda.so),
+against the CPU oracle on the same inputs and against the golden outputs of the compiled reference.
+
+Bars (BASELINE.json north_star):
+  curl field            bit-exact
+  noise field           <= 1e-5 absolute
+  point trajectories    bit-exact here (bar: 1e-4 relative)
+  u8 frames             within +-1 LSB on >= 99.9 % of pixels; bit-exact for k = 1
+"""
+import numpy as np
+import pytest
+
+from conftest import frame_agreement
+
+pytestmark = pytest.mark.gpu
+
+NOISE_TOL = 1e-5
+FRAME_FRACTION = 0.999
+
+
+# ---- generate_simplex ----------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_simplex_golden(ctx, golden, name):
+    dims, amp, freq, seed = golden["meta"][f"simplex_{name}"]["args"]
+    w, h = (int(v) for v in dims.split("x"))
+    out, lo, hi = ctx.generate_simplex(w, h, float(amp), float(freq), int(seed))
+    ref = golden["fields"][f"pot_{name}"]
+    tol = NOISE_TOL * max(1.0, float(amp))
+    assert np.abs(out - ref).max() <= tol
+    assert abs(lo - ref.min()) <= tol and abs(hi - ref.max()) <= tol
+    assert lo == out.min() and hi == out.max()
+
+
+@pytest.mark.parametrize("w,h,freq,seed", [(1000, 500, 8.0, 0), (333, 777, 64.0, 5), (2048, 1024, 4096.0, 9),
+                                            (1, 1, 3.0, 1), (7, 3, 16.0, 2)])
+def test_simplex_vs_oracle(ctx, oracle_mod, w, h, freq, seed):
+    ref, rlo, rhi = oracle_mod.generate_simplex(w, h, 1.0, freq, seed)
+    out, lo, hi = ctx.generate_simplex(w, h, 1.0, freq, seed)
+    assert np.abs(out - ref).max() <= NOISE_TOL
+    assert abs(lo - rlo) <= NOISE_TOL and abs(hi - rhi) <= NOISE_TOL
+
+
+def test_simplex_row_bands_equal_whole(ctx):
+    """Row-sharded generation (how the field is split across GPUs) is bit-identical to one call."""
+    import torch
+    w, h = 640, 200
+    whole, _, _ = ctx.generate_simplex(w, h, 1.0, 8.0, 4)
+    buf = torch.empty((h, w), dtype=torch.float32, device="cuda")
+    for row0, nrows in [(0, 64), (64, 100), (164, 36)]:
+        ctx.generate_simplex_dev(w, h, row0, nrows, 1.0, 8.0, 4, buf.data_ptr() + row0 * w * 4)
+    ctx.sync()
+    assert np.array_equal(buf.cpu().numpy(), whole)
+
+
+# ---- curl_2d ---------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_curl_golden_bit_exact(ctx, golden, name):
+    out, lo, hi = ctx.curl_2d(golden["fields"][f"pot_{name}"])
+    ref = golden["fields"][f"vel_{name}"]
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    assert lo == ref[..., 1].min() and hi == ref.max()
+
+
+@pytest.mark.parametrize("w,h", [(1000, 500), (514, 33), (257, 19), (2, 1), (1, 5), (4096, 64)])
+def test_curl_vs_oracle_bit_exact(ctx, oracle_mod, w, h):
+    rng = np.random.default_rng(w * 31 + h)
+    src = rng.standard_normal((h, w)).astype(np.float32)
+    ref, rlo, rhi = oracle_mod.curl_2d(src)
+    out, lo, hi = ctx.curl_2d(src)
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    assert (lo, hi) == (rlo, rhi)
+
+
+def test_curl_bands_with_halo_row(ctx, oracle_mod):
+    """Row bands with the one-row halo pointer reproduce the single-image result exactly."""
+    import torch
+    rng = np.random.default_rng(1)
+    w, h = 512, 96
+    src = rng.standard_normal((h, w)).astype(np.float32)
+    ref, _, _ = oracle_mod.curl_2d(src)
+    d_src = torch.from_numpy(src).cuda()
+    d_dst = torch.empty((h, w, 2), dtype=torch.float32, device="cuda")
+    bands = [(0, 40), (40, 24), (64, 32)]
+    for row0, nrows in bands:
+        nxt = d_src.data_ptr() + (row0 + nrows) * w * 4 if row0 + nrows < h else None
+        ctx.curl_2d_dev(d_src.data_ptr() + row0 * w * 4, w, nrows, nxt, d_dst.data_ptr() + row0 * w * 8)
+    ctx.sync()
+    assert np.array_equal(d_dst.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+# ---- splat_points / splat_disks --------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["k1_a1", "k3_a1", "k5_a05", "k1_a03", "k7_a1"])
+def test_splat_golden(ctx, golden, name):
+    c = golden["meta"][f"splat_{name}"]
+    pts = golden["splat"]["pts"]
+    ref = golden["splat"][name]
+    if c["k"] == 1 and c["alpha"] == 1.0:
+        img = ctx.splat_points(pts, 96, 64)
+        assert np.array_equal(img, ref)
+        return
+    img = ctx.splat_disks(pts, 96, 64, c["alpha"], c["k"])
+    frac, worst = frame_agreement(img, ref)
+    assert frac >= FRAME_FRACTION and worst <= 1, (frac, worst)
+    if c["k"] == 1:
+        assert np.array_equal(img, ref)
+
+
+@pytest.mark.parametrize("k,alpha,wrap,n,w,h", [
+    (1, 1.0, False, 20000, 300, 200), (3, 1.0, False, 50000, 300, 200), (5, 1.0, True, 30000, 257, 131),
+    (7, 1.0, False, 8000, 130, 70), (3, 0.4, True, 40000, 128, 64), (9, 1.0, False, 5000, 200, 100),
+    (15, 0.8, True, 3000, 100, 90), (3, 1.0, False, 0, 64, 64), (1, 0.5, False, 100000, 33, 17)])
+def test_splat_disks_vs_oracle(ctx, oracle_mod, k, alpha, wrap, n, w, h):
+    rng = np.random.default_rng(k * 1000 + n)
+    pts = ((rng.random((n, 2)) * 1.2 - 0.1) * [w, h]).astype(np.float32)
+    base = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    ref = oracle_mod.splat_disks(pts, w, h, alpha, k, wrap, img=base)
+    img = ctx.splat_disks(pts, w, h, alpha, k, wrapx=wrap, img=base)
+    frac, worst = frame_agreement(img, ref)
+    assert frac >= FRAME_FRACTION, (frac, worst)
+    if k == 1:
+        assert np.array_equal(img, ref)  # a single opacity class replays exactly
+
+
+def test_splat_everything_on_one_pixel(ctx, oracle_mod):
+    """Maximum contention: 200k points on one texel saturate exactly like the sequential loop."""
+    pts = np.full((200000, 2), 20.3, np.float32)
+    for k in (1, 3, 5):
+        ref = oracle_mod.splat_disks(pts, 48, 40, 1.0, k)
+        img = ctx.splat_disks(pts, 48, 40, 1.0, k)
+        assert np.array_equal(img, ref), k
+
+
+def test_splat_weird_coordinates(ctx, oracle_mod):
+    pts = np.array([[np.nan, 3], [3, np.nan], [np.inf, 1], [-np.inf, 1], [1e30, 2], [-1e30, 2], [-0.9, -0.9],
+                    [63.999, 31.999], [64.0, 32.0], [2147483648.0, 5], [-2147483648.0, 5], [4294967296.0, 7]], np.float32)
+    for k in (1, 3):
+        assert np.array_equal(ctx.splat_disks(pts, 64, 32, 1.0, k), oracle_mod.splat_disks(pts, 64, 32, 1.0, k))
+    assert np.array_equal(ctx.splat_points(pts, 64, 32), oracle_mod.splat_points(pts, 64, 32))
+
+
+def test_even_kernel_rejected(ctx):
+    import clumpy_b200
+    with pytest.raises(clumpy_b200.ClumpyCudaError) as e:
+        ctx.splat_disks(np.zeros((1, 2), np.float32), 8, 8, 1.0, 4)
+    assert e.value.code == clumpy_b200.ERR_INVALID and "odd integer" in str(e.value)
+
+
+# ---- advect_points ----------------------------------------------------------------------------
+
+def run_both(ctx, oracle_mod, pts, vel, step, k, decay, nframes, check_every=1):
+    """Steps the oracle and the GPU side by side; returns the worst frame agreement and whether all
+    trajectories were bit-identical at every checked frame."""
+    a = oracle_mod.Advect(pts, vel, step, k, decay, nframes)
+    g = ctx.advect(pts, vel, step, k, decay, nframes)
+    worst_frac, worst_abs, traj_equal = 1.0, 0, True
+    for s in range(2 * nframes):
+        a.step()
+        g.step()
+        if s % check_every == 0 or s == 2 * nframes - 1:
+            traj_equal &= np.array_equal(a.points().view(np.uint32), g.points().view(np.uint32))
+            frac, worst = frame_agreement(g.image(), a.image())
+            worst_frac, worst_abs = min(worst_frac, frac), max(worst_abs, worst)
+    a.close()
+    g.close()
+    return worst_frac, worst_abs, traj_equal
+
+
+@pytest.mark.parametrize("name", ["k1", "k3", "k5", "k7", "k3_wrap", "k1_decay0", "k9"])
+def test_advect_golden(ctx, golden, name):
+    """Whole command through clumpy_cuda_advect_points against the reference CLI's frames."""
+    c = golden["meta"][f"advect_{name}"]
+    adv = golden["advect"]
+    frames = ctx.advect_points(adv["pts"], adv[c["vel"]], c["step"], c["k"], c["decay"], c["nframes"])
+    ref = adv[f"frames_{name}"]
+    assert frames.shape == ref.shape
+    for f in range(len(ref)):
+        frac, worst = frame_agreement(frames[f], ref[f])
+        assert frac >= FRAME_FRACTION, (name, f, frac, worst)
+    if c["k"] == 1:
+        assert np.array_equal(frames, ref)
+
+
+@pytest.mark.parametrize("k,decay,nframes,step", [(1, 0.95, 12, 30.0), (3, 0.99, 8, 60.0), (5, 0.9, 6, 45.0),
+                                                  (7, 0.97, 5, 40.0), (3, -0.95, 8, 80.0), (1, 0.0, 5, 30.0)])
+def test_advect_vs_oracle_stepwise(ctx, oracle_mod, golden, k, decay, nframes, step):
+    vel = golden["fields"]["vel_a"] + np.array([-0.01, 0.004], np.float32)
+    rng = np.random.default_rng(k + nframes)
+    pts = ((rng.random((6000, 2)) * 1.1 - 0.05) * [96, 64]).astype(np.float32)
+    frac, worst, traj = run_both(ctx, oracle_mod, pts, vel, step, k, decay, nframes)
+    assert traj, "trajectories differ from the reference arithmetic"
+    assert frac >= FRAME_FRACTION, (frac, worst)
+    if k == 1:
+        assert frac == 1.0 and worst == 0
+
+
+def test_advect_c1_example5(ctx, oracle_mod, golden):
+    """README example5 at full size: fields from the GPU kernels, frames against the reference md5s
+    (k = 1, so the frames must be bit-identical)."""
+    import hashlib
+    pot, _, _ = ctx.generate_simplex(1000, 500, 1.0, 8.0, 0)
+    ref_pot, _, _ = oracle_mod.generate_simplex(1000, 500, 1.0, 8.0, 0)
+    assert np.abs(pot - ref_pot).max() <= NOISE_TOL
+    vel, _, _ = ctx.curl_2d(ref_pot)  # parity run: same potential as the reference pipeline
+    frames = ctx.advect_points(golden["c1_pts"], vel, 30, 1, 0.95, 240)
+    got = [hashlib.md5(f.tobytes()).hexdigest() for f in frames]
+    assert got == golden["meta"]["c1_frame_data_md5"]
+
+
+def test_advect_dense_k3_long(ctx, oracle_mod):
+    """Several hits per pixel per frame for many frames: the +-1 LSB bound must not drift."""
+    rng = np.random.default_rng(11)
+    w, h, n = 160, 96, 60000  # ~3.9 points per pixel
+    pot, _, _ = oracle_mod.generate_simplex(w, h, 1.0, 3.0, 2)
+    vel, _, _ = oracle_mod.curl_2d(pot)
+    pts = (rng.random((n, 2)) * [w, h]).astype(np.float32)
+    frac, worst, traj = run_both(ctx, oracle_mod, pts, vel, 25.0, 3, 0.99, 40, check_every=5)
+    assert traj
+    assert frac >= FRAME_FRACTION and worst <= 1, (frac, worst)
+
+
+def test_advect_ragged_and_empty(ctx, oracle_mod, golden):
+    vel = golden["fields"]["vel_c"]  # 37 x 50: width not a multiple of 4 (byte path)
+    for n in (0, 1, 2, 3, 255, 257):
+        rng = np.random.default_rng(n)
+        pts = (rng.random((n, 2)) * [50, 37]).astype(np.float32)
+        frac, worst, traj = run_both(ctx, oracle_mod, pts, vel, 3.0, 3, 0.9, 3)
+        assert traj and frac >= FRAME_FRACTION, (n, frac, worst)
+
+
+def test_advect_frame_async_pipeline(ctx, oracle_mod, golden):
+    """frame_async + ping-pong framebuffers deliver the same frames as synchronous reads."""
+    import torch
+    adv = golden["advect"]
+    c = golden["meta"]["advect_k3"]
+    g = ctx.advect(adv["pts"], adv[c["vel"]], c["step"], c["k"], c["decay"], c["nframes"])
+    g.step(c["nframes"])
+    bufs = [torch.empty((64, 96), dtype=torch.uint8).pin_memory() for _ in range(c["nframes"])]
+    for f in range(c["nframes"]):
+        g.step()
+        g.frame_async(bufs[f].data_ptr())
+    g.wait_frames()
+    g.close()
+    ref = adv["frames_k3"]
+    for f in range(c["nframes"]):
+        frac, _ = frame_agreement(bufs[f].numpy(), ref[f])
+        assert frac >= FRAME_FRACTION
+
+
+def test_advect_linearity_of_counts_large(ctx):
+    """Size-independent property at a larger size: with decay 0 and k = 1 every recorded frame is
+    exactly {0, f(0), f(f(0)), ...} per pixel count, so frame pixels only take values from the replay
+    sequence of alpha = 0.5, and pixels without a point are 0; total lit pixels <= npts."""
+    rng = np.random.default_rng(0)
+    w, h, n = 2048, 1024, 400000
+    pts = (rng.random((n, 2)) * [w, h]).astype(np.float32)
+    vel = np.zeros((h, w, 2), np.float32)  # points stay where they are
+    g = ctx.advect(pts, vel, 1.0, 1, 0.0, 2)
+    g.step(3)
+    img = g.image()
+    g.close()
+    counts = np.zeros((h, w), np.int64)
+    np.add.at(counts, (pts[:, 1].astype(np.int64), pts[:, 0].astype(np.int64)), 1)
+    seq = [0]
+    for _ in range(12):
+        seq.append(int(np.float32(np.float32(0.5) * np.float32(seq[-1])) + np.float32(127.5)))
+    lut = np.array(seq + [seq[-1]] * 64)
+    assert np.array_equal(img, lut[np.minimum(counts, len(lut) - 1)].astype(np.uint8))
