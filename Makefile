@@ -11,7 +11,8 @@ ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := $(ARCH) -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -Iinclude \
             -Xcompiler -fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function $(EXTRA_NVFLAGS)
 CSRC     := clumpy_b200/csrc
-CUFILES  := $(CSRC)/context.cu $(CSRC)/simplex.cu $(CSRC)/curl.cu $(CSRC)/splat.cu $(CSRC)/advect.cu
+CUFILES  := $(CSRC)/context.cu $(CSRC)/simplex.cu $(CSRC)/curl.cu $(CSRC)/splat.cu \
+            $(CSRC)/composite_dense.cu $(CSRC)/composite_exact.cu $(CSRC)/advect.cu
 CUOBJS   := $(CUFILES:.cu=.o)
 LIB      := clumpy_b200/libclumpy_cuda.so
 HOST     := clumpy_b200/host
@@ -22,7 +23,7 @@ all: lib cli oracle
 
 lib: $(LIB)
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/internal.h $(CSRC)/device_utils.cuh include/clumpy_cuda.h
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/internal.h $(CSRC)/device_utils.cuh $(CSRC)/rings.cuh include/clumpy_cuda.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(LIB): $(CUOBJS)

@@ -215,7 +215,10 @@ def run_ours(args):
     n, w, h = cfg["npts"], cfg["width"], cfg["height"]
     K, W = args.steps, args.warmup
     hbm_peak, peak_src = measured_peaks()
-    stream = torch.cuda.current_stream()
+    # an explicit (non-null) stream: the library launches on it and torch's events are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = clumpy_b200.Context(local_rank, stream.cuda_stream)
 
     # inputs: field from our own simplex + curl kernels, points from the synthetic recipe (pinned)

@@ -36,7 +36,7 @@
 namespace clumpy {
 
 constexpr int ADVECT_THREADS = 256;
-constexpr int ADVECT_PTS = 2; // points per thread: one 16-byte load/store of positions
+constexpr int ADVECT_PTS = 4; // points per thread (independent load chains in flight)
 
 // ---- the per-frame kernel -----------------------------------------------------------------------
 
@@ -52,44 +52,114 @@ __device__ __forceinline__ float2 euler_step(float2 p, const float2* __restrict_
     return make_float2(__fadd_rn(p.x, __fmul_rn(step, v.x)), __fadd_rn(p.y, __fmul_rn(step, v.y)));
 }
 
-template <bool WRAP, bool SPLAT>
+// How a point is counted into the splat accumulator.
+enum CellMode : int {
+    CELL_NONE = -1, // frame without a splat (warm-up with decay == 0)
+    CELL_U32 = 0,   // 32-bit counters, one RED.ADD per point (any sprite)
+    CELL_U8 = 1,    // byte counters saturating at `cap`, packed 4 per word, CAS loop (dense path)
+    CELL_F16 = 2,   // half-float counters, two per word, one RED.ADD.F16x2 per point: a half counts
+                    // exactly to 2048 and then stays put, so it saturates by itself and cannot carry
+    CELL_X64 = 3,   // 64-bit cells = count (24 bits) + sum of original point indices (40 bits), one
+                    // 64-bit RED.ADD per point: keeps the reference's hit order (composite_exact.cu)
+};
+
+__device__ __forceinline__ void cell_add_f16(uint32_t* __restrict__ words, long long cell) {
+    // (1, 0) or (0, 1) as a half2 bit pattern: 0x3C00 is 1.0
+    const uint32_t one = (cell & 1) ? 0x3C000000u : 0x00003C00u;
+    asm volatile("red.global.add.noftz.f16x2 [%0], %1;" :: "l"(words + (cell >> 1)), "r"(one) : "memory");
+}
+
+// Byte counter += 1, saturating at cap.  The new word is computed from the observed old word, so a
+// cell can never overflow into its neighbour however many threads hit it at once, and once a cell
+// is saturated later points see that with one L2 read and issue no atomic at all.
+//
+// Warp-aggregated: points are stored sorted by tile, so several lanes of a warp usually target the
+// same word (4 neighbouring texels).  Lanes are grouped by word (match.any); the lowest lane of each
+// group adds the group's per-byte counts with ONE compare-and-swap, instead of the lanes fighting
+// each other through retries.  Must be called by all 32 lanes; `cell` < 0 means "no update".
+__device__ __forceinline__ void cell_add_sat_u8(uint32_t* __restrict__ words, long long cell, uint32_t cap) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool valid = cell >= 0;
+    const uint32_t word = valid ? (uint32_t)(cell >> 2) : (0xFFFFFFFFu - lane); // unique key when idle
+    const uint32_t byte = (uint32_t)cell & 3u;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, word);
+    const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, valid && byte == 0u);
+    const uint32_t b1 = __ballot_sync(0xFFFFFFFFu, valid && byte == 1u);
+    const uint32_t b2 = __ballot_sync(0xFFFFFFFFu, valid && byte == 2u);
+    const uint32_t b3 = __ballot_sync(0xFFFFFFFFu, valid && byte == 3u);
+    if (!valid || lane != (uint32_t)(__ffs(peers) - 1)) return;
+    const uint32_t c0 = __popc(peers & b0), c1 = __popc(peers & b1), c2 = __popc(peers & b2), c3 = __popc(peers & b3);
+    uint32_t* w = words + word;
+    uint32_t old = __ldcg(w);
+    for (;;) {
+        const uint32_t n0 = min(cap, (old & 0xFFu) + c0), n1 = min(cap, ((old >> 8) & 0xFFu) + c1);
+        const uint32_t n2 = min(cap, ((old >> 16) & 0xFFu) + c2), n3 = min(cap, (old >> 24) + c3);
+        const uint32_t want = n0 | (n1 << 8) | (n2 << 16) | (n3 << 24);
+        if (want == old) break; // every touched byte is already saturated
+        const uint32_t prev = atomicCAS(w, old, want);
+        if (prev == old) break;
+        old = prev;
+    }
+}
+
+template <bool WRAP, int MODE, typename OffT>
 __global__ void __launch_bounds__(ADVECT_THREADS)
 advect_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
-              const uint32_t* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
+              const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
               uint32_t width, uint32_t height, float step, uint32_t phase, GeomDev g,
-              uint32_t* __restrict__ hist) {
-    const uint32_t i0 = (blockIdx.x * ADVECT_THREADS + threadIdx.x) * ADVECT_PTS;
-    if (i0 >= npts) return;
+              uint32_t* __restrict__ hist, uint32_t cap) {
+    // A CTA owns ADVECT_THREADS * ADVECT_PTS consecutive points; thread t takes t, t + 256, t + 512, ...
+    // so every warp-wide access covers 32 CONSECUTIVE points: position / offset traffic is perfectly
+    // coalesced and, the points being stored in tile order, a warp's gather touches only a few lines.
+    // All loads of a phase are issued before the first use (the kernel is bound by memory latency:
+    // position -> texel -> counter is a dependent chain, so parallelism has to come from the points).
+    const uint32_t base = blockIdx.x * (ADVECT_THREADS * ADVECT_PTS) + threadIdx.x;
+    const uint64_t pol = make_stream_policy();
     float2 p[ADVECT_PTS];
     uint32_t off[ADVECT_PTS];
-    const bool both = i0 + 1 < npts;
-    const uint64_t pol = make_stream_policy();
-    if (both) {
-        const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(pos + i0), pol);
-        p[0] = make_float2(v.x, v.y);
-        p[1] = make_float2(v.z, v.w);
-        const uint2 o = ld_stream_u2(reinterpret_cast<const uint2*>(offset + i0), pol);
-        off[0] = o.x; off[1] = o.y;
-    } else {
-        p[0] = pos[i0];
-        p[1] = p[0];
-        off[0] = offset[i0];
-        off[1] = 0xFFFFFFFFu;
+    bool live[ADVECT_PTS]; // no early return: the byte-cell update below is warp-collective
+#pragma unroll
+    for (int k = 0; k < ADVECT_PTS; ++k) {
+        const uint32_t i = base + k * ADVECT_THREADS;
+        live[k] = i < npts;
+        p[k] = make_float2(0.f, 0.f);
+        off[k] = 0xFFFFFFFFu;
+        if (live[k]) {
+            p[k] = ld_stream_f2(pos + i, pol);
+            off[k] = ld_stream_off(offset + i, pol);
+        }
+    }
+    // nearest-texel fetch (advect_points.cc:23-37): all gathers in flight together
+    float2 v[ADVECT_PTS];
+#pragma unroll
+    for (int k = 0; k < ADVECT_PTS; ++k) {
+        uint32_t x = f2u32_x86(p[k].x);
+        const uint32_t y = f2u32_x86(p[k].y);
+        if (WRAP) x = (width + (x % width)) % width;
+        v[k] = make_float2(0.f, 0.f);
+        if (live[k] && x < width && y < height) v[k] = __ldg(vel + ((size_t)y * width + x));
     }
 #pragma unroll
     for (int k = 0; k < ADVECT_PTS; ++k) {
-        p[k] = euler_step<WRAP>(p[k], vel, width, height, step);
-        if (off[k] == phase) p[k] = orig[i0 + k]; // reset AFTER the move (:147-152,166-170)
+        const uint32_t i = base + k * ADVECT_THREADS;
+        // pt += step * v: rounded multiply, then rounded add (:146)
+        p[k] = make_float2(__fadd_rn(p[k].x, __fmul_rn(step, v[k].x)), __fadd_rn(p[k].y, __fmul_rn(step, v[k].y)));
+        if (off[k] == phase) p[k] = orig[i]; // reset AFTER the move (:147-152,166-170)
+        if (live[k]) st_stream_f2(pos + i, p[k], pol);
     }
-    if (both) st_stream_f4(reinterpret_cast<float4*>(pos + i0), make_float4(p[0].x, p[0].y, p[1].x, p[1].y), pol);
-    else pos[i0] = p[0];
-    if (SPLAT) {
+    if (MODE != CELL_NONE) {
 #pragma unroll
         for (int k = 0; k < ADVECT_PTS; ++k) {
-            if (k == 1 && !both) break;
             // splat_points.cc:143-144: centre texel by (int32_t) truncation
-            const long long at = hist_index<WRAP>(f2i32_x86(p[k].x), f2i32_x86(p[k].y), g);
-            if (at >= 0) atomicAdd(hist + at, 1u);
+            const long long at = live[k] ? hist_index<WRAP>(f2i32_x86(p[k].x), f2i32_x86(p[k].y), g) : -1;
+            if (MODE == CELL_X64) {
+                // exact-order path: the points are in the caller's order, so the slot IS the original index
+                const unsigned long long inc = ((unsigned long long)(base + k * ADVECT_THREADS) << 24) | 1ull;
+                if (at >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(hist) + at, inc);
+            }
+            else if (MODE == CELL_U32) { if (at >= 0) atomicAdd(hist + at, 1u); }
+            else if (MODE == CELL_F16) { if (at >= 0) cell_add_f16(hist, at); }
+            else cell_add_sat_u8(hist, at, cap);
         }
     }
 }
@@ -191,29 +261,34 @@ scan_add_kernel(uint32_t* __restrict__ data, uint32_t n, const uint32_t* __restr
     if (i < n) data[i] += sums[blockIdx.x];
 }
 
-// cursors[] holds the exclusive scan; each point claims the next slot of its tile
+// cursors[] holds the exclusive scan; each point claims the next slot of the tile it is in NOW and
+// takes its whole record (position, home, reset phase, original index) along.
+template <typename OffT>
 __global__ void __launch_bounds__(256)
-sort_scatter_kernel(const float2* __restrict__ pts, const uint32_t* __restrict__ offs, uint32_t npts,
-                    SortGrid sg, uint32_t* __restrict__ cursors, float2* __restrict__ pos,
-                    float2* __restrict__ orig, uint32_t* __restrict__ offset, uint32_t* __restrict__ perm) {
+regroup_scatter_kernel(const float2* __restrict__ pos, const float2* __restrict__ orig,
+                       const OffT* __restrict__ offset, const uint32_t* __restrict__ perm, uint32_t npts,
+                       SortGrid sg, uint32_t* __restrict__ cursors, float2* __restrict__ pos_out,
+                       float2* __restrict__ orig_out, OffT* __restrict__ offset_out,
+                       uint32_t* __restrict__ perm_out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npts) return;
-    const float2 p = pts[i];
+    const float2 p = pos[i];
     const uint32_t slot = atomicAdd(cursors + home_tile(p, sg), 1u);
-    pos[slot] = p;
-    orig[slot] = p;
-    offset[slot] = offs[i];
-    perm[slot] = i;
+    pos_out[slot] = p;
+    orig_out[slot] = orig[i];
+    offset_out[slot] = offset[i];
+    perm_out[slot] = perm[i];
 }
 
+template <typename OffT>
 __global__ void __launch_bounds__(256)
 identity_order_kernel(const float2* __restrict__ pts, const uint32_t* __restrict__ offs, uint32_t npts,
-                      float2* __restrict__ pos, float2* __restrict__ orig, uint32_t* __restrict__ offset,
+                      float2* __restrict__ pos, float2* __restrict__ orig, OffT* __restrict__ offset,
                       uint32_t* __restrict__ perm) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npts) return;
     const float2 p = pts[i];
-    pos[i] = p; orig[i] = p; offset[i] = offs[i]; perm[i] = i;
+    pos[i] = p; orig[i] = p; offset[i] = (OffT)offs[i]; perm[i] = i;
 }
 
 __global__ void __launch_bounds__(256)
@@ -235,7 +310,20 @@ struct clumpy_advect {
     HistGeom geom;
     SpriteRings rings;
     float2 *pos = nullptr, *orig = nullptr, *vel = nullptr;
-    uint32_t *offset = nullptr, *perm = nullptr, *hist = nullptr;
+    void* offset = nullptr;  // uint16_t[npts] when nframes <= 65536 (off16), else uint32_t[npts]
+    bool off16 = false;
+    uint32_t *perm = nullptr;
+    // second copy of the per-point arrays (regroup writes there, then the roles swap) + sort scratch
+    float2 *pos_alt = nullptr, *orig_alt = nullptr;
+    void* offset_alt = nullptr;
+    uint32_t *perm_alt = nullptr, *sort_counts = nullptr, *sort_sums = nullptr;
+    SortGrid sort_grid = {};
+    uint32_t regroup_every = 0, frames_since_regroup = 0; // 0: never regroup
+    uint32_t* hist = nullptr; // counter image: uint32 cells (CELL_U32) or packed byte cells (CELL_U8)
+    int cell_mode = CELL_U32;
+    size_t hist_bytes = 0;
+    DenseTables dense;        // replay tables of the byte-counter path
+    bool l2_window = false;   // an L2 persisting window for the counters is set on the stream
     uint8_t* img[2] = {nullptr, nullptr};
     int cur = 0;                                  // which img holds the current framebuffer
     bool copy_pending[2] = {false, false};        // a frame D2H was issued from img[b]
@@ -245,8 +333,18 @@ struct clumpy_advect {
 
 static void advect_release(clumpy_advect* a) {
     if (!a) return;
+    if (a->l2_window) { // drop the window and give the persisting lines back
+        cudaStreamAttrValue attr = {};
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(a->ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaCtxResetPersistingL2Cache();
+        cudaGetLastError();
+    }
     cudaFree(a->pos); cudaFree(a->orig); cudaFree(a->vel); cudaFree(a->offset); cudaFree(a->perm);
+    cudaFree(a->pos_alt); cudaFree(a->orig_alt); cudaFree(a->offset_alt); cudaFree(a->perm_alt);
+    cudaFree(a->sort_counts); cudaFree(a->sort_sums);
     cudaFree(a->hist); cudaFree(a->img[0]); cudaFree(a->img[1]);
+    free_dense_tables(&a->dense);
     for (int b = 0; b < 2; ++b) if (a->copy_done[b]) cudaEventDestroy(a->copy_done[b]);
     if (a->frame_ready) cudaEventDestroy(a->frame_ready);
     delete a;
@@ -264,20 +362,66 @@ CLUMPY_API int clumpy_cuda_age_offsets(uint32_t nframes, uint32_t npts, uint32_t
     return CLUMPY_OK;
 }
 
+// Counting sort of the per-point records by the image tile each point is in now (asynchronous, on
+// the context's stream).  Used once at set-up (where "now" is "home") and then every
+// `regroup_every` frames: points of one tile share a streamline but not an age (each has its own
+// reset phase), so a fixed order slowly smears every warp's points along ~nframes*speed texels of
+// streamline and the gathers / counter updates lose their locality; regrouping restores it for the
+// price of one extra pass over the points every few dozen frames.  Results do not depend on the order.
+static int regroup_points(clumpy_advect* a) {
+    clumpy_cuda_ctx* ctx = a->ctx;
+    const uint32_t n = a->npts;
+    if (n == 0 || !a->sort_counts) return CLUMPY_OK;
+    const SortGrid& sg = a->sort_grid;
+    const uint32_t pgrid = ceil_div(n, 256), nblocks = ceil_div(sg.ntiles, SCAN_BLOCK);
+    CK(cudaMemsetAsync(a->sort_counts, 0, (size_t)sg.ntiles * 4, ctx->stream));
+    sort_count_kernel<<<pgrid, 256, 0, ctx->stream>>>(a->pos, n, sg, a->sort_counts);
+    CK_LAUNCH(ctx);
+    scan_local_kernel<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(a->sort_counts, sg.ntiles, a->sort_sums);
+    CK_LAUNCH(ctx);
+    scan_sums_kernel<<<1, SCAN_BLOCK, 0, ctx->stream>>>(a->sort_sums, nblocks);
+    CK_LAUNCH(ctx);
+    scan_add_kernel<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(a->sort_counts, sg.ntiles, a->sort_sums);
+    CK_LAUNCH(ctx);
+    if (a->off16)
+        regroup_scatter_kernel<uint16_t><<<pgrid, 256, 0, ctx->stream>>>(
+            a->pos, a->orig, (const uint16_t*)a->offset, a->perm, n, sg, a->sort_counts, a->pos_alt, a->orig_alt,
+            (uint16_t*)a->offset_alt, a->perm_alt);
+    else
+        regroup_scatter_kernel<uint32_t><<<pgrid, 256, 0, ctx->stream>>>(
+            a->pos, a->orig, (const uint32_t*)a->offset, a->perm, n, sg, a->sort_counts, a->pos_alt, a->orig_alt,
+            (uint32_t*)a->offset_alt, a->perm_alt);
+    CK_LAUNCH(ctx);
+    std::swap(a->pos, a->pos_alt);
+    std::swap(a->orig, a->orig_alt);
+    std::swap(a->offset, a->offset_alt);
+    std::swap(a->perm, a->perm_alt);
+    a->frames_since_regroup = 0;
+    return CLUMPY_OK;
+}
+
+// Fills the per-point arrays in the caller's order, sets up the sort grid and does the first regroup.
 static int sort_points(clumpy_advect* a, const float2* d_in, const uint32_t* d_offs) {
     clumpy_cuda_ctx* ctx = a->ctx;
     const uint32_t n = a->npts;
     if (n == 0) return CLUMPY_OK;
     const uint32_t pgrid = ceil_div(n, 256);
+    if (a->off16) identity_order_kernel<uint16_t><<<pgrid, 256, 0, ctx->stream>>>(d_in, d_offs, n, a->pos, a->orig, (uint16_t*)a->offset, a->perm);
+    else identity_order_kernel<uint32_t><<<pgrid, 256, 0, ctx->stream>>>(d_in, d_offs, n, a->pos, a->orig, (uint32_t*)a->offset, a->perm);
+    CK_LAUNCH(ctx);
     const char* no_sort = getenv("CLUMPY_CUDA_NO_SORT");
-    if (no_sort && no_sort[0] == '1') {
-        identity_order_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_in, d_offs, n, a->pos, a->orig, a->offset, a->perm);
-        CK_LAUNCH(ctx);
-        return CLUMPY_OK;
-    }
+    if (no_sort && no_sort[0] == '1') return CLUMPY_OK;
+    if (a->cell_mode == CELL_X64) return CLUMPY_OK; // exact-order path: slot == original index
+
     SortGrid sg;
     sg.width = a->width; sg.height = a->height;
-    sg.shift_x = 3; sg.shift_y = 2; // 8 x 4 texels: one 64-byte run of the velocity field per row
+    // 8 x 4 texels per tile (measured best on B200 among 8x4, 16x2, 16x4, 32x1, 16x1).
+    // CLUMPY_CUDA_SORT_TILE="sx,sy" (log2) overrides (A/B runs).
+    sg.shift_x = 3; sg.shift_y = 2;
+    if (const char* t = getenv("CLUMPY_CUDA_SORT_TILE")) {
+        int sx = 0, sy = 0;
+        if (sscanf(t, "%d,%d", &sx, &sy) == 2 && sx >= 0 && sx < 12 && sy >= 0 && sy < 12) { sg.shift_x = sx; sg.shift_y = sy; }
+    }
     auto tiles = [&](int sx, int sy) {
         return (uint64_t)ceil_div(a->width, 1u << sx) * ceil_div(a->height, 1u << sy);
     };
@@ -286,27 +430,19 @@ static int sort_points(clumpy_advect* a, const float2* d_in, const uint32_t* d_o
     }
     sg.tiles_x = ceil_div(a->width, 1u << sg.shift_x);
     sg.ntiles = (uint32_t)tiles(sg.shift_x, sg.shift_y);
-    const uint32_t nblocks = ceil_div(sg.ntiles, SCAN_BLOCK);
-    uint32_t *counts = nullptr, *sums = nullptr;
-    CK(cudaMalloc(&counts, (size_t)sg.ntiles * 4));
-    if (cudaMalloc(&sums, (size_t)nblocks * 4) != cudaSuccess) { cudaFree(counts); set_error("out of device memory"); return CLUMPY_ERR_NOMEM; }
-    cudaMemsetAsync(counts, 0, (size_t)sg.ntiles * 4, ctx->stream);
-    sort_count_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_in, n, sg, counts);
-    ctx->launches++;
-    scan_local_kernel<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(counts, sg.ntiles, sums);
-    ctx->launches++;
-    scan_sums_kernel<<<1, SCAN_BLOCK, 0, ctx->stream>>>(sums, nblocks);
-    ctx->launches++;
-    scan_add_kernel<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(counts, sg.ntiles, sums);
-    ctx->launches++;
-    sort_scatter_kernel<<<pgrid, 256, 0, ctx->stream>>>(d_in, d_offs, n, sg, counts, a->pos, a->orig, a->offset, a->perm);
-    ctx->launches++;
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(counts);
-    cudaFree(sums);
-    if (e != cudaSuccess) { set_error("point sort failed: %s", cudaGetErrorString(e)); return CLUMPY_ERR_CUDA; }
-    return CLUMPY_OK;
+    a->sort_grid = sg;
+    const size_t nalloc = std::max<size_t>((size_t)n + 1, 2);
+    CK(cudaMalloc(&a->sort_counts, (size_t)sg.ntiles * 4));
+    CK(cudaMalloc(&a->sort_sums, (size_t)ceil_div(sg.ntiles, SCAN_BLOCK) * 4));
+    CK(cudaMalloc(&a->pos_alt, nalloc * 8));
+    CK(cudaMalloc(&a->orig_alt, nalloc * 8));
+    CK(cudaMalloc(&a->offset_alt, nalloc * 4));
+    CK(cudaMalloc(&a->perm_alt, nalloc * 4));
+    // Regroup period: by then about 1/16 of the points have been reset away from their group.
+    // Small clouds do not need it.  CLUMPY_CUDA_REGROUP=<frames> overrides, 0 disables.
+    a->regroup_every = n >= (1u << 16) ? std::max<uint32_t>(8u, a->nframes / 16u) : 0u;
+    if (const char* r = getenv("CLUMPY_CUDA_REGROUP")) a->regroup_every = (uint32_t)atoi(r);
+    return regroup_points(a);
 }
 
 static int advect_begin_impl(clumpy_advect* a, const float* pts_host, const float* vel_host,
@@ -319,12 +455,61 @@ static int advect_begin_impl(clumpy_advect* a, const float* pts_host, const floa
     CK(cudaMalloc(&a->offset, nalloc * 4));
     CK(cudaMalloc(&a->perm, nalloc * 4));
     CK(cudaMalloc(&a->vel, npix * 8));
-    CK(cudaMalloc(&a->hist, a->geom.bytes()));
+    // Counter cells: bytes with replay tables when the sprite allows it (every advect_points sprite
+    // up to k = 7 does), 32-bit counters otherwise.  CLUMPY_CUDA_CELLS=u32 forces the latter (A/B runs).
+    a->off16 = a->nframes <= 65536u;
+    a->cell_mode = CELL_U32;
+    //   auto (default)  sparse cloud (8 * npts <= pixels): exact-order 64-bit cells, points kept in
+    //                   the caller's order; otherwise half-float cells + replay tables, points
+    //                   regrouped by tile; 32-bit cells when the sprite has no tables (k > 7)
+    //   CLUMPY_CUDA_CELLS = exact | f16 | u8 | u32 forces one (A/B runs, tests)
+    {
+        const char* force = getenv("CLUMPY_CUDA_CELLS");
+        std::string want = force ? force : "auto";
+        const bool can_exact = exact_mode_supported(a->kernel_size, a->npts);
+        // Dense clouds: table replay goes ring by ring, which is within 1 LSB when every ring
+        // contracts strongly (k <= 3: opacities 0.65 / 0.5 / 0.35).  Larger sprites have a 0.028 ring;
+        // for them the 32-bit path with its proportionally interleaved replay is the accurate one.
+        if (want == "auto")
+            want = (can_exact && 8ull * a->npts <= (uint64_t)npix) ? "exact" : (a->kernel_size <= 3 ? "f16" : "u32");
+        if (want == "exact" && can_exact) {
+            a->cell_mode = CELL_X64;
+        } else if (want != "u32") {
+            int rc = build_dense_tables(ctx, a->rings, a->decay, &a->dense);
+            if (rc) return rc;
+            if (a->dense.valid) a->cell_mode = (want == "u8") ? CELL_U8 : CELL_F16;
+        }
+    }
+    a->hist_bytes = a->cell_mode == CELL_U8 ? a->geom.cells()
+                  : a->cell_mode == CELL_F16 ? a->geom.cells() * 2
+                  : a->cell_mode == CELL_X64 ? a->geom.cells() * 8 : a->geom.bytes();
+    CK(cudaMalloc(&a->hist, a->hist_bytes));
     CK(cudaMalloc(&a->img[0], npix));
     CK(cudaMalloc(&a->img[1], npix));
     for (int b = 0; b < 2; ++b) CK(cudaEventCreateWithFlags(&a->copy_done[b], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&a->frame_ready, cudaEventDisableTiming));
-    CK(cudaMemsetAsync(a->hist, 0, a->geom.bytes(), ctx->stream));
+    CK(cudaMemsetAsync(a->hist, 0, a->hist_bytes, ctx->stream));
+    // Ask L2 to keep the byte counters: they are touched three times per frame (count, composite,
+    // clear) while ~0.6 GB of streaming point / field traffic passes by.  CLUMPY_CUDA_NO_PERSIST=1
+    // turns this off (A/B runs).
+    {
+        const char* off = getenv("CLUMPY_CUDA_NO_PERSIST");
+        cudaDeviceProp prop;
+        if ((a->cell_mode == CELL_U8 || a->cell_mode == CELL_F16) && !(off && off[0] == '1') &&
+            cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
+            const size_t want = std::min<size_t>(a->hist_bytes, (size_t)prop.persistingL2CacheMaxSize);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaStreamAttrValue attr = {};
+            attr.accessPolicyWindow.base_ptr = a->hist;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(a->hist_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)a->hist_bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+            cudaGetLastError(); // best effort: a refusal only costs bandwidth
+            a->l2_window = true;
+        }
+    }
     CK(cudaMemsetAsync(a->img[0], 0, npix, ctx->stream)); // advect_points.cc:119: zero-initialised
     CK(cudaMemcpyAsync(a->vel, vel_host, npix * 8, cudaMemcpyHostToDevice, ctx->stream));
 
@@ -380,12 +565,28 @@ CLUMPY_API int clumpy_cuda_advect_begin(clumpy_cuda_ctx* ctx, const float* pts_h
     return CLUMPY_OK;
 }
 
-template <bool WRAP, bool SPLAT>
-static void launch_advect(clumpy_advect* a, uint32_t phase) {
+template <bool WRAP, int MODE, typename OffT>
+static void launch_advect_t(clumpy_advect* a, uint32_t phase) {
     const uint32_t grid = ceil_div(a->npts, ADVECT_THREADS * ADVECT_PTS);
     const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch};
-    advect_kernel<WRAP, SPLAT><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
-        a->pos, a->orig, a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase, g, a->hist);
+    advect_kernel<WRAP, MODE, OffT><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
+        a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase, g,
+        a->hist, a->dense.cell_cap);
+}
+
+template <bool WRAP, int MODE>
+static void launch_advect_m(clumpy_advect* a, uint32_t phase) {
+    if (a->off16) launch_advect_t<WRAP, MODE, uint16_t>(a, phase);
+    else launch_advect_t<WRAP, MODE, uint32_t>(a, phase);
+}
+
+template <bool WRAP>
+static void launch_advect(clumpy_advect* a, uint32_t phase, bool splat) {
+    if (!splat) launch_advect_m<WRAP, CELL_NONE>(a, phase);
+    else if (a->cell_mode == CELL_U8) launch_advect_m<WRAP, CELL_U8>(a, phase);
+    else if (a->cell_mode == CELL_F16) launch_advect_m<WRAP, CELL_F16>(a, phase);
+    else if (a->cell_mode == CELL_X64) launch_advect_m<WRAP, CELL_X64>(a, phase);
+    else launch_advect_m<WRAP, CELL_U32>(a, phase);
 }
 
 // ev (optional): 4 events recorded before the advect kernel, after it, after the composite kernel and
@@ -398,8 +599,8 @@ static int advect_one_frame(clumpy_advect* a, cudaEvent_t* ev = nullptr) {
     const uint32_t phase = s % a->nframes;
     if (ev) CK(cudaEventRecord(ev[0], ctx->stream));
     if (a->npts) {
-        if (a->wrapx) { if (splat) launch_advect<true, true>(a, phase); else launch_advect<true, false>(a, phase); }
-        else          { if (splat) launch_advect<false, true>(a, phase); else launch_advect<false, false>(a, phase); }
+        if (a->wrapx) launch_advect<true>(a, phase, splat);
+        else launch_advect<false>(a, phase, splat);
         CK_LAUNCH(ctx);
     }
     if (ev) CK(cudaEventRecord(ev[1], ctx->stream));
@@ -413,16 +614,26 @@ static int advect_one_frame(clumpy_advect* a, cudaEvent_t* ev = nullptr) {
                 a->copy_pending[dst] = false;
             }
         }
-        int rc = launch_composite(ctx, a->geom, a->rings, a->hist, a->wrapx, 1, a->decay, a->img[a->cur], a->img[dst]);
+        int rc;
+        if (a->cell_mode == CELL_U8)
+            rc = launch_composite_dense(ctx, a->geom, a->dense, reinterpret_cast<const uint8_t*>(a->hist), a->wrapx,
+                                        a->img[a->cur], a->img[dst]);
+        else if (a->cell_mode == CELL_F16)
+            rc = launch_composite_half(ctx, a->geom, a->dense, a->hist, a->wrapx, a->img[a->cur], a->img[dst]);
+        else if (a->cell_mode == CELL_X64)
+            rc = launch_composite_exact(ctx, a->geom, a->rings, a->hist, a->wrapx, 1, a->decay, a->img[a->cur], a->img[dst]);
+        else
+            rc = launch_composite(ctx, a->geom, a->rings, a->hist, a->wrapx, 1, a->decay, a->img[a->cur], a->img[dst]);
         if (rc) return rc;
         a->cur = dst;
         if (ev) CK(cudaEventRecord(ev[2], ctx->stream));
-        CK(cudaMemsetAsync(a->hist, 0, a->geom.bytes(), ctx->stream));
+        CK(cudaMemsetAsync(a->hist, 0, a->hist_bytes, ctx->stream));
     } else if (ev) {
         CK(cudaEventRecord(ev[2], ctx->stream));
     }
     if (ev) CK(cudaEventRecord(ev[3], ctx->stream));
     a->simframe = s + 1;
+    if (a->regroup_every && ++a->frames_since_regroup >= a->regroup_every) return regroup_points(a);
     return CLUMPY_OK;
 }
 

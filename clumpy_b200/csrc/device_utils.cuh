@@ -113,6 +113,21 @@ __device__ __forceinline__ uint2 ld_stream_u2(const uint2* p, uint64_t pol) {
                  : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
     return v;
 }
+__device__ __forceinline__ uint32_t ld_stream_u1(const uint32_t* p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_off(const uint32_t* p, uint64_t pol) { return ld_stream_u1(p, pol); }
+__device__ __forceinline__ uint32_t ld_stream_off(const uint16_t* p, uint64_t pol) {
+    uint16_t v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f2(float2* p, float2 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void st_stream_f4(float4* p, float4 v, uint64_t pol) {
     asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");

@@ -78,7 +78,8 @@ struct HistGeom {
     int halo = 0;              // h = kernel_size / 2
     int pitch = 0;             // counters per padded row
     int rows = 0;              // padded rows
-    size_t bytes() const { return (size_t)pitch * rows * sizeof(uint32_t); }
+    size_t cells() const { return (size_t)pitch * rows; }
+    size_t bytes() const { return cells() * sizeof(uint32_t); }
 };
 HistGeom make_hist_geom(uint32_t width, uint32_t height, int kernel_size);
 
@@ -92,6 +93,43 @@ struct SpriteRings {
     uint8_t tap_class[CLUMPY_MAX_KERNEL_SIZE * CLUMPY_MAX_KERNEL_SIZE]; // per tap (i + j*k); 255 = skip
 };
 int make_sprite_rings(int kernel_size, float alpha, SpriteRings* out);
+
+// ---- dense path: u8 saturating counters + replay tables (composite_dense.cu) ------------------
+//
+// For the sprites advect_points uses (opacity 1) every ring's truncating blend f_a becomes
+// stationary after a small number of applications for ALL 256 start values (12 for k = 3, 88 at
+// most).  So a counter only has to count up to that depth: cells are bytes that saturate at
+// `cell_cap` (packed 4 per word, updated with a compare-and-swap loop), the counter image is W*H
+// bytes and stays resident in L2, and the composite pass replaces the replay loop by one lookup per
+// ring in a table of iterated blends T_r[n][d] = f_a^n(d) held in shared memory.
+struct DenseTables {
+    bool valid = false;      // false: some ring needs more than cell_cap applications -> use u32 cells
+    int kernel_size = 0;
+    int nring = 0;
+    int depth[16] = {0};     // number of table rows of ring r (0: ring has opacity 0, skipped)
+    int row0[16] = {0};      // first row of ring r; row 0 of the block is the decay table
+    int nrows = 0;
+    uint32_t cell_cap = 255; // saturation value of a cell
+    bool byte_lanes = false; // ring sums of 4 pixels fit the 4 bytes of one register
+    uint8_t* d_rows = nullptr; // nrows * 256 bytes, device
+};
+int build_dense_tables(clumpy_cuda_ctx* ctx, const SpriteRings& rings, float decay, DenseTables* out);
+void free_dense_tables(DenseTables* t);
+int launch_composite_dense(clumpy_cuda_ctx* ctx, const HistGeom& g, const DenseTables& t,
+                           const uint8_t* d_cells, int wrapx, const uint8_t* d_img_in,
+                           uint8_t* d_img_out);
+
+// same pass for counters stored as half floats (fire-and-forget red.add.f16x2 on the advect side)
+int launch_composite_half(clumpy_cuda_ctx* ctx, const HistGeom& g, const DenseTables& t,
+                          const void* d_cells, int wrapx, const uint8_t* d_img_in, uint8_t* d_img_out);
+
+// ---- exact-order path for sparse clouds (composite_exact.cu): 64-bit cells = count + index sum ----
+bool exact_mode_supported(int kernel_size, uint64_t npts);
+int launch_exact_count(clumpy_cuda_ctx* ctx, const float* d_pts, uint32_t npts, const HistGeom& g,
+                       int wrapx, void* d_cells);
+int launch_composite_exact(clumpy_cuda_ctx* ctx, const HistGeom& g, const SpriteRings& rings,
+                           const void* d_cells, int wrapx, int apply_decay, float decay,
+                           const uint8_t* d_img_in, uint8_t* d_img_out);
 
 // counts AoS points (x, y) into hist
 int launch_hist_points(clumpy_cuda_ctx* ctx, const float* d_pts, uint32_t npts, const HistGeom& g,

@@ -26,6 +26,7 @@
 // reduced mod W first and the composite pass reads its halo columns mod W.
 #include "device_utils.cuh"
 #include "internal.h"
+#include "rings.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -46,7 +47,7 @@ HistGeom make_hist_geom(uint32_t width, uint32_t height, int kernel_size) {
     g.height = (int)height;
     g.halo = kernel_size / 2;
     g.pitch = (int)(round_up(width, TILE_W) + round_up(2 * g.halo, 4) + 4);
-    g.rows = (int)(round_up(height, TILE_H) + 2 * g.halo);
+    g.rows = (int)(round_up(height, 16) + 2 * g.halo); // 16 = tallest composite tile
     return g;
 }
 
@@ -120,6 +121,52 @@ __device__ __forceinline__ uint32_t replay(uint32_t d, float a, uint32_t n) {
     return d;
 }
 
+// Replays n[r] hits of opacity alpha[r], r < NR, INTERLEAVED in proportion: at step s the ring that
+// is furthest behind its share s * n[r] / total goes next.  As far as one pixel is concerned the
+// reference's point order is a random interleaving of the rings; ring-by-ring replay (all strong hits
+// first, weak ones last) is the extreme case and accumulates the most truncation bias when the
+// opacities are weak, the proportional interleave is the typical one.  With a single active ring this
+// is the plain replay (bit-exact).  Stops when every ring still owed hits leaves the value unchanged.
+template <int NR>
+__device__ __forceinline__ uint32_t replay_mixed(uint32_t d, const float* __restrict__ alpha, const uint32_t (&n)[NR]) {
+    uint32_t rem[NR], total = 0u, active = 0u;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        rem[r] = (alpha[r] != 0.0f) ? n[r] : 0u;
+        total += rem[r];
+        if (rem[r]) active |= 1u << r;
+    }
+    if (total == 0u) return d;
+    if ((active & (active - 1u)) == 0u) { // one ring only
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+            if (active == (1u << r)) d = replay(d, alpha[r], rem[r]);
+        return d;
+    }
+    const float inv = 1.0f / (float)total;
+    float share[NR], done[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) { share[r] = (float)rem[r] * inv; done[r] = 0.0f; }
+    uint32_t stalled = 0u;
+    for (uint32_t s = 1u; active; ++s) {
+        int best = 0;
+        float best_score = -3.0e38f;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const float score = fmaf((float)s, share[r], -done[r]);
+            if (((active >> r) & 1u) && score > best_score) { best_score = score; best = r; }
+        }
+        float a = 0.0f;
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+            if (best == r) { a = alpha[r]; done[r] += 1.0f; if (--rem[r] == 0u) active &= ~(1u << r); }
+        const uint32_t nd = blend_once(d, __fsub_rn(1.0f, a), __fmul_rn(a, 255.0f));
+        if (nd == d) stalled |= 1u << best; else { d = nd; stalled = 0u; }
+        if ((active & ~stalled) == 0u) break;
+    }
+    return d;
+}
+
 // advect_points.cc:155,174: `v *= decay` on a uint8_t&
 __device__ __forceinline__ uint32_t decay_once(uint32_t d, float decay) {
     return f2u8_x86(__fmul_rn((float)d, decay));
@@ -149,26 +196,6 @@ int launch_hist_points(clumpy_cuda_ctx* ctx, const float* d_pts, uint32_t npts, 
 }
 
 // ---- composite pass -----------------------------------------------------------------------------
-
-// Compile-time map tap (i, j) -> rank of its squared distance among the distinct distances of a
-// K x K sprite (the same ranking make_sprite_rings uses on the host).
-template <int K>
-struct RingTable {
-    int8_t ring[K * K];
-    int nring;
-    constexpr RingTable() : ring{}, nring(0) {
-        constexpr int H = K / 2;
-        int n = 0;
-        for (int d2 = 0; d2 <= 2 * H * H; ++d2) {
-            bool found = false;
-            for (int j = 0; j < K; ++j)
-                for (int i = 0; i < K; ++i)
-                    if ((i - H) * (i - H) + (j - H) * (j - H) == d2) { ring[i + j * K] = (int8_t)n; found = true; }
-            if (found) ++n;
-        }
-        nring = n;
-    }
-};
 
 struct RingAlpha { float a[16]; };
 
@@ -258,9 +285,7 @@ composite_kernel(GeomDev g, RingAlpha ra, const uint32_t* __restrict__ hist, int
     for (int j = 0; j < 4; ++j) {
         uint32_t d = px[j];
         if (apply_decay) d = decay_once(d, decay);
-#pragma unroll
-        for (int r = 0; r < RT.nring; ++r) d = replay(d, ra.a[r], cnt[j][r]);
-        px[j] = d;
+        px[j] = replay_mixed<RT.nring>(d, ra.a, cnt[j]);
     }
     if (full) {
         *reinterpret_cast<uchar4*>(img_out + at) = make_uchar4((uint8_t)px[0], (uint8_t)px[1], (uint8_t)px[2], (uint8_t)px[3]);
@@ -314,8 +339,7 @@ composite_generic_kernel(GeomDev g, GenericSprite sp, const uint32_t* __restrict
         const size_t at = (size_t)y * g.width + x;
         uint32_t d = img_in[at];
         if (apply_decay) d = decay_once(d, decay);
-        for (int c = 0; c < sp.nclass; ++c) d = replay(d, sp.class_alpha[c], cnt[c]);
-        img_out[at] = (uint8_t)d;
+        img_out[at] = (uint8_t)replay_mixed<16>(d, sp.class_alpha, cnt); // unused classes have opacity 0
     }
 }
 
@@ -419,15 +443,30 @@ CLUMPY_API int clumpy_cuda_splat_disks(clumpy_cuda_ctx* ctx, const float* pts_ho
     const HistGeom g = make_hist_geom(width, height, kernel_size);
     SplatBuffers b;
     const size_t npix = (size_t)width * height;
+    // Sparse list (8 * npts <= pixels): 64-bit cells that keep the reference's hit order
+    // (composite_exact.cu).  Dense list: 32-bit counts, ring-order replay.  CLUMPY_CUDA_CELLS=u32 /
+    // exact forces one of the two.
+    bool exact = exact_mode_supported(kernel_size, npts) && 8ull * npts <= (uint64_t)npix;
+    if (const char* force = getenv("CLUMPY_CUDA_CELLS")) {
+        if (!strcmp(force, "u32")) exact = false;
+        if (!strcmp(force, "exact")) exact = exact_mode_supported(kernel_size, npts);
+    }
+    const size_t hist_bytes = exact ? g.cells() * 8 : g.bytes();
     CK(cudaMalloc(&b.pts, std::max<size_t>(8, (size_t)npts * 8)));
     CK(cudaMalloc(&b.img, npix));
-    CK(cudaMalloc(&b.hist, g.bytes()));
+    CK(cudaMalloc(&b.hist, hist_bytes));
     CK(cudaMemcpyAsync(b.pts, pts_host, (size_t)npts * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(b.img, img_host, npix, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(b.hist, 0, g.bytes(), ctx->stream));
-    rc = launch_hist_points(ctx, b.pts, npts, g, wrapx, b.hist);
-    if (rc) return rc;
-    rc = launch_composite(ctx, g, rings, b.hist, wrapx, /*apply_decay=*/0, 1.0f, b.img, b.img);
+    CK(cudaMemsetAsync(b.hist, 0, hist_bytes, ctx->stream));
+    if (exact) {
+        rc = launch_exact_count(ctx, b.pts, npts, g, wrapx, b.hist);
+        if (rc) return rc;
+        rc = launch_composite_exact(ctx, g, rings, b.hist, wrapx, /*apply_decay=*/0, 1.0f, b.img, b.img);
+    } else {
+        rc = launch_hist_points(ctx, b.pts, npts, g, wrapx, b.hist);
+        if (rc) return rc;
+        rc = launch_composite(ctx, g, rings, b.hist, wrapx, /*apply_decay=*/0, 1.0f, b.img, b.img);
+    }
     if (rc) return rc;
     CK(cudaMemcpyAsync(img_host, b.img, npix, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
