@@ -58,6 +58,12 @@ SIGNATURES = {
                                            C.c_int, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "clumpy_cuda_advect_step": (C.c_int, [C.c_void_p, C.c_uint32]),
     "clumpy_cuda_advect_profile": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _f32p, _f32p]),
+    "clumpy_cuda_advect_count": (C.c_int, [C.c_void_p]),
+    "clumpy_cuda_advect_cells": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                           _u32p, _u32p, _u32p, _u32p]),
+    "clumpy_cuda_advect_composite_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "clumpy_cuda_advect_finish_frame": (C.c_int, [C.c_void_p]),
+    "clumpy_cuda_advect_image_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "clumpy_cuda_advect_simframe": (C.c_int, [C.c_void_p, _u32p]),
     "clumpy_cuda_advect_frame_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "clumpy_cuda_advect_wait_frames": (C.c_int, [C.c_void_p]),
@@ -281,6 +287,31 @@ class Advect:
         s = C.c_uint32()
         _check(lib().clumpy_cuda_advect_simframe(self._h, C.byref(s)))
         return s.value
+
+    # ---- one frame split at the exchange point (multi-GPU, see clumpy_b200/multigpu.py) -----------
+
+    def count(self):
+        _check(lib().clumpy_cuda_advect_count(self._h))
+
+    def cells(self):
+        """-> (device address, bytes, pitch in cells, rows, halo, bytes per cell) of the private
+        counter image the last count() wrote."""
+        p, nbytes = C.c_void_p(), C.c_size_t()
+        pitch, rows, halo, bpc = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(lib().clumpy_cuda_advect_cells(self._h, C.byref(p), C.byref(nbytes), C.byref(pitch),
+                                              C.byref(rows), C.byref(halo), C.byref(bpc)))
+        return p.value, nbytes.value, pitch.value, rows.value, halo.value, bpc.value
+
+    def composite_rows(self, cells_dev, row0, nrows):
+        _check(lib().clumpy_cuda_advect_composite_rows(self._h, _vp(cells_dev), row0, nrows))
+
+    def finish_frame(self):
+        _check(lib().clumpy_cuda_advect_finish_frame(self._h))
+
+    def image_dev(self):
+        p = C.c_void_p()
+        _check(lib().clumpy_cuda_advect_image_dev(self._h, C.byref(p)))
+        return p.value
 
     def frame_async(self, dst):
         _check(lib().clumpy_cuda_advect_frame_async(self._h, _vp(dst)))

@@ -63,10 +63,20 @@ enum CellMode : int {
                     // 64-bit RED.ADD per point: keeps the reference's hit order (composite_exact.cu)
 };
 
-__device__ __forceinline__ void cell_add_f16(uint32_t* __restrict__ words, long long cell) {
+__device__ __forceinline__ void cell_add_f16(uint32_t* __restrict__ words, long long cell, uint64_t keep) {
     // (1, 0) or (0, 1) as a half2 bit pattern: 0x3C00 is 1.0
     const uint32_t one = (cell & 1) ? 0x3C000000u : 0x00003C00u;
-    asm volatile("red.global.add.noftz.f16x2 [%0], %1;" :: "l"(words + (cell >> 1)), "r"(one) : "memory");
+    asm volatile("red.global.add.L2::cache_hint.noftz.f16x2 [%0], %1, %2;"
+                 :: "l"(words + (cell >> 1)), "r"(one), "l"(keep) : "memory");
+}
+
+// Zeroes a counter image with evict-last stores (cudaMemset would leave the lines with normal
+// priority and they would be gone from L2 before the next frame counts into them).
+__global__ void __launch_bounds__(256)
+clear_cells_kernel(uint4* __restrict__ p, size_t n16) {
+    const uint64_t keep = make_keep_policy();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        st_hint_u4(p + i, make_uint4(0u, 0u, 0u, 0u), keep);
 }
 
 // Byte counter += 1, saturating at cap.  The new word is computed from the observed old word, so a
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS)
 advect_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
               const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
               uint32_t width, uint32_t height, float step, uint32_t phase, GeomDev g,
-              uint32_t* __restrict__ hist, uint32_t cap) {
+              uint32_t* __restrict__ hist, uint32_t cap, int keep_cells) {
     // A CTA owns ADVECT_THREADS * ADVECT_PTS consecutive points; thread t takes t, t + 256, t + 512, ...
     // so every warp-wide access covers 32 CONSECUTIVE points: position / offset traffic is perfectly
     // coalesced and, the points being stored in tile order, a warp's gather touches only a few lines.
@@ -115,6 +125,7 @@ advect_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
     // position -> texel -> counter is a dependent chain, so parallelism has to come from the points).
     const uint32_t base = blockIdx.x * (ADVECT_THREADS * ADVECT_PTS) + threadIdx.x;
     const uint64_t pol = make_stream_policy();
+    const uint64_t keep = keep_cells ? make_keep_policy() : make_normal_policy();
     float2 p[ADVECT_PTS];
     uint32_t off[ADVECT_PTS];
     bool live[ADVECT_PTS]; // no early return: the byte-cell update below is warp-collective
@@ -158,7 +169,7 @@ advect_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                 if (at >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(hist) + at, inc);
             }
             else if (MODE == CELL_U32) { if (at >= 0) atomicAdd(hist + at, 1u); }
-            else if (MODE == CELL_F16) { if (at >= 0) cell_add_f16(hist, at); }
+            else if (MODE == CELL_F16) { if (at >= 0) cell_add_f16(hist, at, keep); }
             else cell_add_sat_u8(hist, at, cap);
         }
     }
@@ -319,9 +330,18 @@ struct clumpy_advect {
     uint32_t *perm_alt = nullptr, *sort_counts = nullptr, *sort_sums = nullptr;
     SortGrid sort_grid = {};
     uint32_t regroup_every = 0, frames_since_regroup = 0; // 0: never regroup
-    uint32_t* hist = nullptr; // counter image: uint32 cells (CELL_U32) or packed byte cells (CELL_U8)
+    uint32_t* hist = nullptr; // the allocation: two counter images back to back (see CellMode)
+    uint32_t* hist_buf[2] = {nullptr, nullptr}; // frame s counts into hist_buf[cellbuf]
+    int cellbuf = 0;
     int cell_mode = CELL_U32;
-    size_t hist_bytes = 0;
+    size_t hist_bytes = 0;    // bytes of ONE counter image
+    // overlap: composite + clear of frame s on ctx->aux_stream while advect of frame s+1 runs on
+    // ctx->stream.  advected[b]: counts of buffer b complete; cleared[b]: buffer b zeroed again.
+    bool overlap = false, side_dirty = false;
+    bool keep_cells = false;  // half-float counters are accessed with L2 evict-last hints
+    bool count_open = false;  // advect_count was called, advect_finish_frame not yet
+    bool clear_pending[2] = {false, false};
+    cudaEvent_t advected[2] = {nullptr, nullptr}, cleared[2] = {nullptr, nullptr}, side_done = nullptr;
     DenseTables dense;        // replay tables of the byte-counter path
     bool l2_window = false;   // an L2 persisting window for the counters is set on the stream
     uint8_t* img[2] = {nullptr, nullptr};
@@ -345,8 +365,13 @@ static void advect_release(clumpy_advect* a) {
     cudaFree(a->sort_counts); cudaFree(a->sort_sums);
     cudaFree(a->hist); cudaFree(a->img[0]); cudaFree(a->img[1]);
     free_dense_tables(&a->dense);
-    for (int b = 0; b < 2; ++b) if (a->copy_done[b]) cudaEventDestroy(a->copy_done[b]);
+    for (int b = 0; b < 2; ++b) {
+        if (a->copy_done[b]) cudaEventDestroy(a->copy_done[b]);
+        if (a->advected[b]) cudaEventDestroy(a->advected[b]);
+        if (a->cleared[b]) cudaEventDestroy(a->cleared[b]);
+    }
     if (a->frame_ready) cudaEventDestroy(a->frame_ready);
+    if (a->side_done) cudaEventDestroy(a->side_done);
     delete a;
 }
 
@@ -483,29 +508,55 @@ static int advect_begin_impl(clumpy_advect* a, const float* pts_host, const floa
     a->hist_bytes = a->cell_mode == CELL_U8 ? a->geom.cells()
                   : a->cell_mode == CELL_F16 ? a->geom.cells() * 2
                   : a->cell_mode == CELL_X64 ? a->geom.cells() * 8 : a->geom.bytes();
-    CK(cudaMalloc(&a->hist, a->hist_bytes));
+    // Two counter images: while frame s is composited and its image cleared on the side stream,
+    // frame s+1 already counts into the other one.  CLUMPY_CUDA_OVERLAP=0 runs everything on one
+    // stream (A/B runs); small clouds gain nothing from the overlap and skip it.
+    {
+        const char* ov = getenv("CLUMPY_CUDA_OVERLAP");
+        a->overlap = ov ? (ov[0] != '0') : (a->npts >= (1u << 18));
+        const char* kc = getenv("CLUMPY_CUDA_KEEP_CELLS");
+        // L2 evict-last hints on the counters: measured to make no difference on B200 (0.2132 vs
+        // 0.2173 ms per step), so off unless asked for.
+        a->keep_cells = a->cell_mode == CELL_F16 && (kc ? kc[0] != '0' : false);
+        ctx->keep_cells = a->keep_cells ? 1 : 0;
+        if (const char* cap = getenv("CLUMPY_CUDA_COMPOSITE_CTAS")) ctx->composite_ctas_per_sm = atoi(cap);
+        else ctx->composite_ctas_per_sm = a->overlap ? 4 : 0;
+    }
+    const size_t image_stride = round_up(a->hist_bytes, 256);
+    CK(cudaMalloc(&a->hist, 2 * image_stride));
+    a->hist_buf[0] = a->hist;
+    a->hist_buf[1] = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(a->hist) + image_stride);
     CK(cudaMalloc(&a->img[0], npix));
     CK(cudaMalloc(&a->img[1], npix));
-    for (int b = 0; b < 2; ++b) CK(cudaEventCreateWithFlags(&a->copy_done[b], cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+        CK(cudaEventCreateWithFlags(&a->copy_done[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&a->advected[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&a->cleared[b], cudaEventDisableTiming));
+    }
     CK(cudaEventCreateWithFlags(&a->frame_ready, cudaEventDisableTiming));
-    CK(cudaMemsetAsync(a->hist, 0, a->hist_bytes, ctx->stream));
-    // Ask L2 to keep the byte counters: they are touched three times per frame (count, composite,
-    // clear) while ~0.6 GB of streaming point / field traffic passes by.  CLUMPY_CUDA_NO_PERSIST=1
-    // turns this off (A/B runs).
+    CK(cudaEventCreateWithFlags(&a->side_done, cudaEventDisableTiming));
+    CK(cudaMemsetAsync(a->hist, 0, 2 * image_stride, ctx->stream));
+    // Optional (CLUMPY_CUDA_PERSIST=1): an L2 persisting window over the counters, which are touched
+    // three times per frame while ~0.6 GB of streaming traffic passes by.  Measured on B200 it is a
+    // wash for one 64 MB image (0.165 vs 0.178 ms advect) and a 2.3x LOSS for the two images of the
+    // overlapped schedule, because the carve-out is taken away from the velocity field's share of L2;
+    // so it is off by default.
     {
-        const char* off = getenv("CLUMPY_CUDA_NO_PERSIST");
+        const char* on = getenv("CLUMPY_CUDA_PERSIST");
         cudaDeviceProp prop;
-        if ((a->cell_mode == CELL_U8 || a->cell_mode == CELL_F16) && !(off && off[0] == '1') &&
+        if ((a->cell_mode == CELL_U8 || a->cell_mode == CELL_F16) && (on && on[0] == '1') &&
             cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
-            const size_t want = std::min<size_t>(a->hist_bytes, (size_t)prop.persistingL2CacheMaxSize);
+            const size_t window = std::min<size_t>(2 * image_stride, (size_t)prop.accessPolicyMaxWindowSize);
+            const size_t want = std::min<size_t>(window, (size_t)prop.persistingL2CacheMaxSize);
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
             cudaStreamAttrValue attr = {};
             attr.accessPolicyWindow.base_ptr = a->hist;
-            attr.accessPolicyWindow.num_bytes = std::min<size_t>(a->hist_bytes, (size_t)prop.accessPolicyMaxWindowSize);
-            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)a->hist_bytes);
+            attr.accessPolicyWindow.num_bytes = window;
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)window);
             attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+            cudaStreamSetAttribute(ctx->aux_stream, cudaStreamAttributeAccessPolicyWindow, &attr);
             cudaGetLastError(); // best effort: a refusal only costs bandwidth
             a->l2_window = true;
         }
@@ -558,6 +609,12 @@ CLUMPY_API int clumpy_cuda_advect_begin(clumpy_cuda_ctx* ctx, const float* pts_h
     a->ctx = ctx; a->npts = npts; a->width = width; a->height = height; a->nframes = nframes;
     a->kernel_size = kernel_size; a->wrapx = wrapx ? 1 : 0; a->step_size = step_size; a->decay = decay;
     a->geom = make_hist_geom(width, height, kernel_size);
+    // Multi-GPU callers split the counter image into equal row bands (one per rank, whole 16-row
+    // tiles): they ask for the padded row count to be a multiple of 16 * world_size.
+    if (const char* m = getenv("CLUMPY_CUDA_CELL_ROWS_MULTIPLE")) {
+        const int mult = atoi(m);
+        if (mult > 1 && mult <= (1 << 20)) a->geom.rows = (int)round_up((size_t)a->geom.rows, (size_t)mult);
+    }
     a->rings = rings;
     rc = advect_begin_impl(a, pts_host, vel_host, age_offset);
     if (rc) { advect_release(a); return rc; }
@@ -571,7 +628,7 @@ static void launch_advect_t(clumpy_advect* a, uint32_t phase) {
     const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch};
     advect_kernel<WRAP, MODE, OffT><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
         a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase, g,
-        a->hist, a->dense.cell_cap);
+        a->hist_buf[a->cellbuf], a->dense.cell_cap, a->keep_cells ? 1 : 0);
 }
 
 template <bool WRAP, int MODE>
@@ -597,43 +654,84 @@ static int advect_one_frame(clumpy_advect* a, cudaEvent_t* ev = nullptr) {
     const bool warm = s < a->nframes;
     const bool splat = !(warm && a->decay == 0.0f); // advect_points.cc:154
     const uint32_t phase = s % a->nframes;
-    if (ev) CK(cudaEventRecord(ev[0], ctx->stream));
+    // Frame s counts into image b on the main stream; its composite + clear run on `side`, which is
+    // the high-priority aux stream when overlapping (so they share the SMs with the advect kernel
+    // of frame s+1) and the main stream otherwise (and always while profiling with events).
+    const bool overlap = a->overlap && !ev;
+    const cudaStream_t main_stream = ctx->stream;
+    const cudaStream_t side = overlap ? ctx->aux_stream : main_stream;
+    const int b = a->cellbuf;
+    uint32_t* const cells = a->hist_buf[b];
+    if (splat && a->clear_pending[b]) { // image b was last used two frames ago: wait for its clear
+        CK(cudaStreamWaitEvent(main_stream, a->cleared[b], 0));
+        a->clear_pending[b] = false;
+    }
+    if (ev) CK(cudaEventRecord(ev[0], main_stream));
     if (a->npts) {
         if (a->wrapx) launch_advect<true>(a, phase, splat);
         else launch_advect<false>(a, phase, splat);
         CK_LAUNCH(ctx);
     }
-    if (ev) CK(cudaEventRecord(ev[1], ctx->stream));
+    if (ev) CK(cudaEventRecord(ev[1], main_stream));
     if (splat) {
+        if (overlap) {
+            CK(cudaEventRecord(a->advected[b], main_stream));
+            CK(cudaStreamWaitEvent(side, a->advected[b], 0));
+        }
         // write in place unless a frame copy is still reading the current buffer
         int dst = a->cur;
         if (a->copy_pending[a->cur]) {
             dst = a->cur ^ 1;
             if (a->copy_pending[dst]) {
-                CK(cudaStreamWaitEvent(ctx->stream, a->copy_done[dst], 0));
+                CK(cudaStreamWaitEvent(side, a->copy_done[dst], 0));
                 a->copy_pending[dst] = false;
             }
         }
+        ctx->stream = side; // the launchers enqueue on ctx->stream
         int rc;
         if (a->cell_mode == CELL_U8)
-            rc = launch_composite_dense(ctx, a->geom, a->dense, reinterpret_cast<const uint8_t*>(a->hist), a->wrapx,
+            rc = launch_composite_dense(ctx, a->geom, a->dense, reinterpret_cast<const uint8_t*>(cells), a->wrapx,
                                         a->img[a->cur], a->img[dst]);
         else if (a->cell_mode == CELL_F16)
-            rc = launch_composite_half(ctx, a->geom, a->dense, a->hist, a->wrapx, a->img[a->cur], a->img[dst]);
+            rc = launch_composite_half(ctx, a->geom, a->dense, cells, a->wrapx, a->img[a->cur], a->img[dst]);
         else if (a->cell_mode == CELL_X64)
-            rc = launch_composite_exact(ctx, a->geom, a->rings, a->hist, a->wrapx, 1, a->decay, a->img[a->cur], a->img[dst]);
+            rc = launch_composite_exact(ctx, a->geom, a->rings, cells, a->wrapx, 1, a->decay, a->img[a->cur], a->img[dst]);
         else
-            rc = launch_composite(ctx, a->geom, a->rings, a->hist, a->wrapx, 1, a->decay, a->img[a->cur], a->img[dst]);
+            rc = launch_composite(ctx, a->geom, a->rings, cells, a->wrapx, 1, a->decay, a->img[a->cur], a->img[dst]);
+        ctx->stream = main_stream;
         if (rc) return rc;
         a->cur = dst;
-        if (ev) CK(cudaEventRecord(ev[2], ctx->stream));
-        CK(cudaMemsetAsync(a->hist, 0, a->hist_bytes, ctx->stream));
+        if (ev) CK(cudaEventRecord(ev[2], main_stream));
+        if (a->keep_cells && a->hist_bytes % 16 == 0) {
+            const size_t n16 = a->hist_bytes / 16;
+            const uint32_t grid = (uint32_t)std::min<size_t>((n16 + 255) / 256, (size_t)ctx->sm_count * 8);
+            clear_cells_kernel<<<grid, 256, 0, side>>>(reinterpret_cast<uint4*>(cells), n16);
+            CK_LAUNCH(ctx);
+        } else {
+            CK(cudaMemsetAsync(cells, 0, a->hist_bytes, side));
+        }
+        if (overlap) {
+            CK(cudaEventRecord(a->cleared[b], side));
+            a->clear_pending[b] = true;
+            a->side_dirty = true;
+            a->cellbuf = b ^ 1;
+        }
     } else if (ev) {
-        CK(cudaEventRecord(ev[2], ctx->stream));
+        CK(cudaEventRecord(ev[2], main_stream));
     }
-    if (ev) CK(cudaEventRecord(ev[3], ctx->stream));
+    if (ev) CK(cudaEventRecord(ev[3], main_stream));
     a->simframe = s + 1;
     if (a->regroup_every && ++a->frames_since_regroup >= a->regroup_every) return regroup_points(a);
+    return CLUMPY_OK;
+}
+
+// Makes the main stream wait for everything issued on the side stream, so that whatever the caller
+// enqueues (or records) on the context's stream next is ordered after the whole frame.
+static int advect_join(clumpy_advect* a) {
+    if (!a->side_dirty) return CLUMPY_OK;
+    CK(cudaEventRecord(a->side_done, a->ctx->aux_stream));
+    CK(cudaStreamWaitEvent(a->ctx->stream, a->side_done, 0));
+    a->side_dirty = false;
     return CLUMPY_OK;
 }
 
@@ -644,7 +742,7 @@ CLUMPY_API int clumpy_cuda_advect_step(clumpy_advect* adv, uint32_t count) {
         int rc = advect_one_frame(adv);
         if (rc) return rc;
     }
-    return CLUMPY_OK;
+    return advect_join(adv);
 }
 
 CLUMPY_API int clumpy_cuda_advect_profile(clumpy_advect* adv, uint32_t count, float* advect_ms,
@@ -669,6 +767,84 @@ CLUMPY_API int clumpy_cuda_advect_profile(clumpy_advect* adv, uint32_t count, fl
     if (composite_ms) *composite_ms = (float)(t[1] / count);
     if (clear_ms) *clear_ms = (float)(t[2] / count);
     return rc;
+}
+
+// ---- one frame split at the exchange point (multi-GPU: points sharded, counters summed) ----------
+
+static bool frame_splats(const clumpy_advect* a) {
+    return !(a->simframe < a->nframes && a->decay == 0.0f); // advect_points.cc:154
+}
+
+CLUMPY_API int clumpy_cuda_advect_count(clumpy_advect* adv) {
+    REQUIRE(adv, "adv is NULL");
+    clumpy_cuda_ctx* ctx = adv->ctx;
+    CK(cudaSetDevice(ctx->device));
+    int rc = advect_join(adv);
+    if (rc) return rc;
+    REQUIRE(!adv->count_open, "advect_count called twice without advect_finish_frame");
+    const bool splat = frame_splats(adv);
+    if (splat && adv->clear_pending[adv->cellbuf]) {
+        CK(cudaStreamWaitEvent(ctx->stream, adv->cleared[adv->cellbuf], 0));
+        adv->clear_pending[adv->cellbuf] = false;
+    }
+    if (adv->npts) {
+        const uint32_t phase = adv->simframe % adv->nframes;
+        if (adv->wrapx) launch_advect<true>(adv, phase, splat);
+        else launch_advect<false>(adv, phase, splat);
+        CK_LAUNCH(ctx);
+    }
+    adv->count_open = true;
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_advect_cells(clumpy_advect* adv, void** cells_dev, size_t* bytes,
+                                        uint32_t* pitch_cells, uint32_t* rows, uint32_t* halo,
+                                        uint32_t* bytes_per_cell) {
+    REQUIRE(adv, "adv is NULL");
+    if (cells_dev) *cells_dev = adv->hist_buf[adv->cellbuf];
+    if (bytes) *bytes = adv->hist_bytes;
+    if (pitch_cells) *pitch_cells = (uint32_t)adv->geom.pitch;
+    if (rows) *rows = (uint32_t)adv->geom.rows;
+    if (halo) *halo = (uint32_t)adv->geom.halo;
+    if (bytes_per_cell)
+        *bytes_per_cell = adv->cell_mode == CELL_U8 ? 1u : adv->cell_mode == CELL_F16 ? 2u : adv->cell_mode == CELL_X64 ? 8u : 4u;
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_advect_composite_rows(clumpy_advect* adv, const void* cells_dev,
+                                                 uint32_t row0, uint32_t nrows) {
+    REQUIRE(adv && cells_dev, "null argument");
+    REQUIRE((uint64_t)row0 + nrows <= adv->height, "row band exceeds the image");
+    clumpy_cuda_ctx* ctx = adv->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (!frame_splats(adv) || nrows == 0) return CLUMPY_OK;
+    // the band as an image of its own: same width and pitch, `nrows` rows, cells given by the caller
+    HistGeom g = adv->geom;
+    g.height = (int)nrows;
+    uint8_t* img = adv->img[adv->cur] + (size_t)row0 * adv->width;
+    if (adv->cell_mode == CELL_U8)
+        return launch_composite_dense(ctx, g, adv->dense, reinterpret_cast<const uint8_t*>(cells_dev), adv->wrapx, img, img);
+    if (adv->cell_mode == CELL_F16) return launch_composite_half(ctx, g, adv->dense, cells_dev, adv->wrapx, img, img);
+    if (adv->cell_mode == CELL_X64) return launch_composite_exact(ctx, g, adv->rings, cells_dev, adv->wrapx, 1, adv->decay, img, img);
+    return launch_composite(ctx, g, adv->rings, reinterpret_cast<const uint32_t*>(cells_dev), adv->wrapx, 1, adv->decay, img, img);
+}
+
+CLUMPY_API int clumpy_cuda_advect_image_dev(clumpy_advect* adv, void** img_dev) {
+    REQUIRE(adv && img_dev, "null argument");
+    *img_dev = adv->img[adv->cur];
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_advect_finish_frame(clumpy_advect* adv) {
+    REQUIRE(adv, "adv is NULL");
+    REQUIRE(adv->count_open, "advect_finish_frame without advect_count");
+    clumpy_cuda_ctx* ctx = adv->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (frame_splats(adv)) CK(cudaMemsetAsync(adv->hist_buf[adv->cellbuf], 0, adv->hist_bytes, ctx->stream));
+    adv->count_open = false;
+    adv->simframe += 1;
+    if (adv->regroup_every && ++adv->frames_since_regroup >= adv->regroup_every) return regroup_points(adv);
+    return CLUMPY_OK;
 }
 
 CLUMPY_API int clumpy_cuda_advect_simframe(clumpy_advect* adv, uint32_t* simframe) {

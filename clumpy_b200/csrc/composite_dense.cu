@@ -231,6 +231,7 @@ static int launch_dense_k(clumpy_cuda_ctx* ctx, const GeomDev& g, const DenseTab
     if (per_sm < 1) { set_error("dense composite kernel does not fit on an SM"); return CLUMPY_ERR_CUDA; }
     const int tiles_x = (int)ceil_div(g.width, DTILE_W), tiles_y = (int)ceil_div(g.height, DTILE_H);
     const int ntiles = tiles_x * tiles_y;
+    if (ctx->composite_ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->composite_ctas_per_sm);
     const int grid = std::min(ntiles, per_sm * ctx->sm_count);
     const int vec_ok = (g.width % 4 == 0) && ((uintptr_t)in % 4 == 0) && ((uintptr_t)out % 4 == 0);
     kern<<<grid, DENSE_THREADS, smem, ctx->stream>>>(g, dp, t.d_rows, cells, in, out, tiles_x, ntiles, vec_ok);
@@ -270,8 +271,9 @@ template <int K, bool WRAP>
 __global__ void __launch_bounds__(DENSE_THREADS)
 composite_half_kernel(GeomDev g, DenseParams dp, const uint8_t* __restrict__ tables_g,
                       const __half* __restrict__ cells, const uint8_t* __restrict__ img_in,
-                      uint8_t* __restrict__ img_out, int tiles_x, int ntiles, int vec_ok) {
+                      uint8_t* __restrict__ img_out, int tiles_x, int ntiles, int vec_ok, int keep_cells) {
     using HS = HalfShape<K>;
+    const uint64_t cell_policy = keep_cells ? make_keep_policy() : make_normal_policy();
     constexpr int H = HS::H;
     constexpr RingTable<K> RT{};
     extern __shared__ __align__(16) uint8_t smem[];
@@ -294,7 +296,7 @@ composite_half_kernel(GeomDev g, DenseParams dp, const uint8_t* __restrict__ tab
             for (int r = warp; r < HS::ROWS; r += DENSE_THREADS / 32) {
                 const uint32_t* src = reinterpret_cast<const uint32_t*>(cells + (size_t)(ty0 + r) * g.pitch + tx0);
 #pragma unroll
-                for (int c = lane; c < LOADW; c += 32) tile[r * HS::ROWW + c] = __ldcg(src + c);
+                for (int c = lane; c < LOADW; c += 32) tile[r * HS::ROWW + c] = ld_hint_u32(src + c, cell_policy);
             }
         } else {
             __half* th = reinterpret_cast<__half*>(tile);
@@ -390,9 +392,10 @@ static int launch_half_k(clumpy_cuda_ctx* ctx, const GeomDev& g, const DenseTabl
     if (per_sm < 1) { set_error("half-cell composite kernel does not fit on an SM"); return CLUMPY_ERR_CUDA; }
     const int tiles_x = (int)ceil_div(g.width, DTILE_W), tiles_y = (int)ceil_div(g.height, DTILE_H);
     const int ntiles = tiles_x * tiles_y;
+    if (ctx->composite_ctas_per_sm > 0) per_sm = std::min(per_sm, ctx->composite_ctas_per_sm);
     const int grid = std::min(ntiles, per_sm * ctx->sm_count);
     const int vec_ok = (g.width % 4 == 0) && ((uintptr_t)in % 4 == 0) && ((uintptr_t)out % 4 == 0);
-    kern<<<grid, DENSE_THREADS, smem, ctx->stream>>>(g, dp, t.d_rows, cells, in, out, tiles_x, ntiles, vec_ok);
+    kern<<<grid, DENSE_THREADS, smem, ctx->stream>>>(g, dp, t.d_rows, cells, in, out, tiles_x, ntiles, vec_ok, ctx->keep_cells);
     CK_LAUNCH(ctx);
     return CLUMPY_OK;
 }

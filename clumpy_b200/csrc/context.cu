@@ -90,6 +90,11 @@ CLUMPY_API int clumpy_cuda_create(int device, void* stream, clumpy_cuda_ctx** ou
         ctx->own_stream = true;
     }
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    {
+        int least = 0, greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, greatest));
+    }
     CK(cudaEventCreate(&ctx->t0));
     CK(cudaEventCreate(&ctx->t1));
     CK(cudaMalloc(&ctx->d_minmax, 8));
@@ -103,8 +108,10 @@ CLUMPY_API void clumpy_cuda_destroy(clumpy_cuda_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->aux_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
+    cudaStreamDestroy(ctx->aux_stream);
     cudaEventDestroy(ctx->t0);
     cudaEventDestroy(ctx->t1);
     cudaFree(ctx->d_minmax);
@@ -116,6 +123,7 @@ CLUMPY_API int clumpy_cuda_sync(clumpy_cuda_ctx* ctx) {
     REQUIRE(ctx, "ctx is NULL");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->aux_stream));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     return CLUMPY_OK;
 }

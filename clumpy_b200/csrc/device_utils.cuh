@@ -95,6 +95,27 @@ __device__ __forceinline__ uint64_t make_stream_policy() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+// The opposite hint for the splat counters: touched three times per frame (count, composite, clear)
+// with ~0.6 GB of streaming traffic in between, so ask L2 to evict them last.
+__device__ __forceinline__ uint64_t make_keep_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t make_normal_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint32_t ld_hint_u32(const uint32_t* p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_hint_u4(uint4* p, uint4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p, uint64_t pol) {
     float4 v;
     asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"

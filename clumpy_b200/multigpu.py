@@ -1,0 +1,279 @@
+"""advect_points across the GPUs of one box: one process per GPU, torch.distributed for the plumbing.
+
+What shards and what does not (BASELINE.json north_star):
+
+  points      advect independently        -> contiguous index ranges, one per rank; no communication
+  velocity    read at random by every point -> replicated on every GPU
+  splat       every rank counts ITS points into a private counter image (one cell per texel);
+              the images are summed across ranks each frame and every rank composites (decay +
+              replay + u8) the row band it owns.  The sum is a reduce-scatter by bands of padded
+              rows over NCCL / NVLink, plus an all-gather of the 2*halo edge rows each band needs
+              from its neighbours.
+  frames      stay distributed: rank g holds image rows owned_rows(g); gather_image() assembles them.
+
+The host-side plan (who owns which points and rows) is plain Python and is exercised on CPU with the
+gloo backend in tests/test_multigpu_cpu.py; the device work goes through the C ABI
+(clumpy_cuda_advect_count / _cells / _composite_rows / _finish_frame).
+"""
+import json
+import os
+import time
+
+import numpy as np
+
+CELL_ROW_MULTIPLE = 16  # composite tiles are 16 rows tall
+
+
+def shard_range(n, world, rank):
+    """Contiguous, balanced index range of rank `rank` among `world` for n items."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+class BandPlan:
+    """Row bands of the padded counter image (rows_alloc = world * chunk rows)."""
+
+    def __init__(self, height, halo, rows_alloc, world):
+        if rows_alloc % world:
+            raise ValueError("the counter image must have a multiple of world_size rows")
+        if rows_alloc < height + 2 * halo:
+            raise ValueError("the counter image is too small for the framebuffer")
+        self.height, self.halo, self.rows_alloc, self.world = height, halo, rows_alloc, world
+        self.chunk = rows_alloc // world
+        if world > 1 and self.chunk < 2 * halo:
+            raise ValueError("bands thinner than the sprite are not supported")
+
+    def padded_rows(self, rank):
+        """Padded rows [lo, hi) that rank `rank` receives from the reduce-scatter."""
+        return rank * self.chunk, (rank + 1) * self.chunk
+
+    def owned_rows(self, rank):
+        """Image rows [y0, y1) whose pixels rank `rank` composites: those whose whole window of
+        2*halo+1 padded rows lies in the rank's chunk plus its two halos."""
+        lo, hi = self.padded_rows(rank)
+        y0, y1 = max(0, lo - self.halo), min(self.height, hi - self.halo)
+        return (y0, max(y0, y1))
+
+    def band_buffer_rows(self):
+        """Rows of the per-rank band buffer: halo above + chunk + halo below + tile slack."""
+        return self.chunk + 2 * self.halo + 2 * CELL_ROW_MULTIPLE
+
+    def cell_row_offset(self, rank):
+        """Row of the band buffer that holds padded row owned_rows(rank)[0] (= the cells of image row
+        y0 - halo): what composite_rows wants a pointer to."""
+        lo, _ = self.padded_rows(rank)
+        y0, _ = self.owned_rows(rank)
+        return y0 - (lo - self.halo)
+
+
+def exchange_counts(private, band, plan, rank, dist, scratch=None):
+    """Sums the private counter images of all ranks and leaves rank `rank`'s band (chunk + halos) in
+    `band` (rows: halo | chunk | halo | slack).  `private` is (rows_alloc, pitch), `band` is
+    (band_buffer_rows, pitch); both torch tensors on the rank's device (or CPU for the gloo tests)."""
+    import torch
+    h, chunk, world = plan.halo, plan.chunk, plan.world
+    mid = band[h:h + chunk]
+    if world == 1:
+        mid.copy_(private[:chunk])
+    elif private.is_cuda:
+        dist.reduce_scatter_tensor(mid, private, op=dist.ReduceOp.SUM)
+    else:  # gloo has no reduce-scatter: all-reduce a copy and keep our rows (tests only)
+        tmp = private.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM)
+        mid.copy_(tmp[rank * chunk:(rank + 1) * chunk])
+    if h == 0:
+        return
+    band[:h].zero_()
+    band[h + chunk:h + chunk + h].zero_()
+    if world == 1:
+        return
+    edges = torch.cat([mid[:h], mid[chunk - h:chunk]])  # my first and last h rows
+    gathered = torch.empty((world,) + tuple(edges.shape), dtype=edges.dtype, device=edges.device) \
+        if scratch is None else scratch
+    dist.all_gather_into_tensor(gathered, edges) if private.is_cuda else \
+        dist.all_gather(list(gathered.unbind(0)), edges)
+    if rank > 0:
+        band[:h].copy_(gathered[rank - 1, h:2 * h])          # previous band's last rows
+    if rank < world - 1:
+        band[h + chunk:h + chunk + h].copy_(gathered[rank + 1, :h])  # next band's first rows
+
+
+class _DeviceView:
+    """Lets torch alias library-owned device memory (no copy) through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2}
+
+
+_TYPESTR = {1: ("|u1", "uint8"), 2: ("<f2", "float16"), 4: ("<i4", "int32")}
+
+
+class ShardedAdvect:
+    """advect_points with the points of one run spread over torch.distributed ranks."""
+
+    def __init__(self, ctx, pts, vel, step_size, kernel_size, decay, nframes, dist, device):
+        import torch
+        import clumpy_b200
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.ctx, self.device = ctx, device
+        self.h_img, self.w_img = vel.shape[:2]
+        n = len(pts)
+        lo, hi = shard_range(n, self.world, self.rank)
+        offsets = clumpy_b200.age_offsets(nframes, n)[lo:hi]  # offsets follow the GLOBAL point index
+        # count-only cells (the exact-order cells carry local indices); rows padded so that every
+        # rank gets a whole number of 16-row tiles
+        os.environ["CLUMPY_CUDA_CELLS"] = "f16" if kernel_size <= 3 else "u32"
+        os.environ["CLUMPY_CUDA_OVERLAP"] = "0"
+        os.environ["CLUMPY_CUDA_CELL_ROWS_MULTIPLE"] = str(CELL_ROW_MULTIPLE * self.world)
+        self.adv = ctx.advect(np.ascontiguousarray(pts[lo:hi]), vel, step_size, kernel_size, decay, nframes,
+                              age_offset=offsets)
+        self.npts_local = hi - lo
+        ptr, nbytes, pitch, rows, halo, bpc = self.adv.cells()
+        typestr, tname = _TYPESTR[bpc]
+        self.plan = BandPlan(self.h_img, halo, rows, self.world)
+        self.private = torch.as_tensor(_DeviceView(ptr, (rows, pitch), typestr), device=device)
+        self.band = torch.zeros((self.plan.band_buffer_rows(), pitch), dtype=getattr(torch, tname), device=device)
+        self.scratch = torch.empty((self.world, 2 * halo, pitch), dtype=self.band.dtype, device=device) if halo else None
+        self.y0, self.y1 = self.plan.owned_rows(self.rank)
+        self.band_ptr = self.band.data_ptr() + self.plan.cell_row_offset(self.rank) * pitch * bpc
+
+    def step(self, count=1):
+        for _ in range(count):
+            self.adv.count()
+            exchange_counts(self.private, self.band, self.plan, self.rank, self.dist, self.scratch)
+            self.adv.composite_rows(self.band_ptr, self.y0, self.y1 - self.y0)
+            self.adv.finish_frame()
+
+    def band_image(self):
+        """This rank's rows of the current framebuffer as a (rows, W) uint8 torch tensor (a view)."""
+        img = self.torch.as_tensor(_DeviceView(self.adv.image_dev(), (self.h_img, self.w_img), "|u1"), device=self.device)
+        return img[self.y0:self.y1]
+
+    def gather_image(self):
+        """The whole framebuffer on every rank (numpy), assembled from the bands."""
+        torch, dist = self.torch, self.dist
+        full = torch.zeros((self.h_img, self.w_img), dtype=torch.uint8, device=self.device)
+        full[self.y0:self.y1].copy_(self.band_image())
+        if self.world > 1:
+            dist.all_reduce(full, op=dist.ReduceOp.SUM)  # bands are disjoint
+        return full.cpu().numpy()
+
+    def points(self):
+        """All positions in the caller's order (numpy), gathered from the shards."""
+        torch, dist = self.torch, self.dist
+        mine = torch.from_numpy(self.adv.points()).to(self.device)
+        if self.world == 1:
+            return mine.cpu().numpy()
+        sizes = [shard_range(self._n_total(), self.world, r) for r in range(self.world)]
+        parts = [torch.empty((hi - lo, 2), dtype=torch.float32, device=self.device) for lo, hi in sizes]
+        dist.all_gather(parts, mine)
+        return torch.cat(parts).cpu().numpy()
+
+    def _n_total(self):
+        t = self.torch.tensor([self.npts_local], device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return int(t.item())
+
+    def close(self):
+        self.adv.close()
+
+
+def bench_multi(args, cfg, workload, metric, unit):
+    """bench.py body for --gpus N > 1 (launched by torch.distributed.run, one rank per GPU)."""
+    import torch
+    import torch.distributed as dist
+    import clumpy_b200
+    from bench import ALGO_BYTES_PER_PIXEL_FRAME, ALGO_BYTES_PER_POINT_STEP, ClockSampler, measured_peaks, synth_points
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=device)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = clumpy_b200.Context(local_rank, stream.cuda_stream)
+    n, w, h = cfg["npts"], cfg["width"], cfg["height"]
+    K, W = args.steps, args.warmup
+    hbm_peak, peak_src = measured_peaks()
+
+    # every rank builds the (replicated) field with the library's own kernels; points come from the
+    # same seeded recipe on every rank and are sliced by the sharded run
+    d_pot = torch.empty((h, w), dtype=torch.float32, device=device)
+    d_vel = torch.empty((h, w, 2), dtype=torch.float32, device=device)
+    ctx.generate_simplex_dev(w, h, 0, h, cfg["amplitude"], cfg["frequency"], cfg["seed"], d_pot.data_ptr())
+    ctx.curl_2d_dev(d_pot.data_ptr(), w, h, None, d_vel.data_ptr())
+    vel = torch.empty((h, w, 2), dtype=torch.float32).pin_memory()
+    vel.copy_(d_vel)
+    torch.cuda.synchronize()
+    del d_pot, d_vel
+    pts = synth_points(n, w, h)
+
+    run = ShardedAdvect(ctx, pts, vel.numpy(), cfg["step_size"], cfg["kernel_size"], cfg["decay"], cfg["nframes"],
+                        dist, device)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    run.step(W)
+    dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    run.step(K)
+    e1.record(stream)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # slowest rank
+    ms = float(ms.item())
+    launches = ctx.launch_count() - launches0
+    value = n * K / (ms * 1e-3)
+
+    # e2e: every rank also copies its band of each recorded frame to pinned host memory
+    y0, y1 = run.y0, run.y1
+    host_band = [torch.empty((max(1, y1 - y0), w), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    nrec = max(1, K // 2)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run2 = ShardedAdvect(ctx, pts, vel.numpy(), cfg["step_size"], cfg["kernel_size"], cfg["decay"], nrec, dist, device)
+    run2.step(nrec)
+    for f in range(nrec):
+        run2.step(1)
+        if y1 > y0:
+            host_band[f & 1][:y1 - y0].copy_(run2.band_image(), non_blocking=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=device)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    run2.close()
+    run.close()
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        e2e_steps = 2 * nrec
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32+u8", "data": "synthetic",
+            "config": {"workload": workload, "frames_per_s": K / (ms * 1e-3),
+                       "parallelism": f"points sharded x{world}, field replicated, per-frame NCCL reduce-scatter of the "
+                                      "f16 counter image by row bands + halo all-gather, band composite per rank",
+                       "l2": "inputs larger than L2 (field 268 MB per GPU)"},
+            "clocks": clocks,
+            "e2e": {"value": n * e2e_steps / dt, "unit": unit,
+                    "h2d_bytes_per_step": (n * 12 + world * w * h * 8) / e2e_steps, "d2h_bytes_per_step": nrec * w * h / e2e_steps,
+                    "steps": e2e_steps, "seconds": dt,
+                    "what": "per rank: H2D of its point shard + the whole field, sort, frames, D2H of its row band of "
+                            "every recorded frame to pinned memory"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "whole step (all ranks)", "peak": hbm_peak * world, "unit": "GB/s",
+                         "achieved": (n * ALGO_BYTES_PER_POINT_STEP + w * h * ALGO_BYTES_PER_PIXEL_FRAME) / (ms / K * 1e-3) / 1e9,
+                         "frac": (n * ALGO_BYTES_PER_POINT_STEP + w * h * ALGO_BYTES_PER_PIXEL_FRAME) / (ms / K * 1e-3) / 1e9 / (hbm_peak * world),
+                         "traffic": None, "peak_source": peak_src},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line))
+    ctx.close()
+    dist.destroy_process_group()
+    return 0

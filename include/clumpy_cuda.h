@@ -141,6 +141,34 @@ int clumpy_cuda_advect_step(clumpy_advect* adv, uint32_t count);
 int clumpy_cuda_advect_profile(clumpy_advect* adv, uint32_t count, float* advect_ms,
                                float* composite_ms, float* clear_ms);
 
+/* ---- one simulation frame split at its exchange point (multi-GPU) ------------------------------
+ * Points advect independently, so they are sharded across GPUs, each with the whole velocity field.
+ * What the shards share is the splat: every GPU counts ITS points into a private counter image (one
+ * cell per texel, padded by kernel_size/2 on every side), the images are summed across GPUs (NCCL,
+ * by the caller), and each GPU composites the rows it owns.  One frame is then
+ *
+ *     clumpy_cuda_advect_count          Euler step + reset + count of this GPU's points
+ *     clumpy_cuda_advect_cells          where that counter image is (device pointer, geometry)
+ *     ... caller sums the images across GPUs (all-reduce, or reduce-scatter by row bands) ...
+ *     clumpy_cuda_advect_composite_rows decay + splat replay for image rows [row0, row0+nrows)
+ *     clumpy_cuda_advect_finish_frame   clears the private image, advances the frame counter
+ *
+ * Counter images are row-major with `pitch_cells` cells per row; the cell of texel (x, y) is at
+ * [(y + halo) * pitch + (x + halo)].  composite_rows takes a pointer to the padded row `row0` (the
+ * cells of image row row0 - halo) of an image with that pitch that holds at least
+ * round_up(nrows, 16) + 2*halo rows from there; it updates the framebuffer rows in place. */
+int clumpy_cuda_advect_count(clumpy_advect* adv);
+int clumpy_cuda_advect_cells(clumpy_advect* adv, void** cells_dev, size_t* bytes,
+                             uint32_t* pitch_cells, uint32_t* rows, uint32_t* halo,
+                             uint32_t* bytes_per_cell);
+int clumpy_cuda_advect_composite_rows(clumpy_advect* adv, const void* cells_dev, uint32_t row0,
+                                      uint32_t nrows);
+int clumpy_cuda_advect_finish_frame(clumpy_advect* adv);
+
+/* Device address of the current framebuffer (height * width u8), for callers that gather row
+ * bands across GPUs themselves. */
+int clumpy_cuda_advect_image_dev(clumpy_advect* adv, void** img_dev);
+
 /* Number of simulation frames done so far; frames [nframes, 2*nframes) are the recorded ones. */
 int clumpy_cuda_advect_simframe(clumpy_advect* adv, uint32_t* simframe);
 

@@ -7,6 +7,8 @@ Bars (BASELINE.json north_star):
   point trajectories    bit-exact here (bar: 1e-4 relative)
   u8 frames             within +-1 LSB on >= 99.9 % of pixels; bit-exact for k = 1
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -344,3 +346,38 @@ def test_advect_linearity_of_counts_large(ctx):
         seq.append(int(np.float32(np.float32(0.5) * np.float32(seq[-1])) + np.float32(127.5)))
     lut = np.array(seq + [seq[-1]] * 64)
     assert np.array_equal(img, lut[np.minimum(counts, len(lut) - 1)].astype(np.uint8))
+
+
+# ---- multi-GPU path, single rank (the N-rank run is tools/check_multigpu.py under torchrun) ----------
+
+def test_sharded_advect_world_of_one(ctx, oracle_mod, golden):
+    """The count / exchange / composite-rows / finish split used across GPUs, run with a process group
+    of one rank: must agree with the oracle like the fused path does."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    from clumpy_b200.multigpu import ShardedAdvect
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                            device_id=torch.device("cuda", 0))
+    try:
+        rng = np.random.default_rng(9)
+        vel = golden["fields"]["vel_a"] + np.array([-0.01, 0.004], np.float32)
+        pts = ((rng.random((9000, 2)) * 1.1 - 0.05) * [96, 64]).astype(np.float32)
+        for k, decay in [(3, 0.97), (1, 0.9), (5, 0.95)]:
+            run = ShardedAdvect(ctx, pts, vel, 50.0, k, decay, 6, dist, torch.device("cuda", 0))
+            ref = oracle_mod.Advect(pts, vel, 50.0, k, decay, 6)
+            for s_ in range(12):
+                run.step()
+                ref.step()
+                frac, worst = frame_agreement(run.gather_image(), ref.image())
+                assert frac >= FRAME_FRACTION, (k, s_, frac, worst)
+            assert np.array_equal(run.points().view(np.uint32), ref.points().view(np.uint32))
+            run.close()
+            ref.close()
+    finally:
+        dist.destroy_process_group()
+        for v in ("CLUMPY_CUDA_CELLS", "CLUMPY_CUDA_OVERLAP", "CLUMPY_CUDA_CELL_ROWS_MULTIPLE"):
+            os.environ.pop(v, None)

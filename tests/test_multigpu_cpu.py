@@ -1,0 +1,81 @@
+"""Host-side logic of the multi-GPU path, on CPU: point sharding, the row-band plan, and the counter
+exchange (reduce-scatter by bands + halo all-gather) run for real over torch.distributed with the gloo
+backend and world_size 2 and 3.  No CUDA here; the device kernels are covered by the gpu tests."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from clumpy_b200.multigpu import BandPlan, exchange_counts, shard_range
+
+
+def test_shard_range_covers_everything():
+    for n in (0, 1, 7, 16, 12392, 1 << 24):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("height,halo,world", [(4096, 1, 8), (500, 0, 2), (500, 2, 3), (64, 3, 2), (2000, 3, 4), (37, 1, 2)])
+def test_band_plan_partitions_the_image(height, halo, world):
+    rows_alloc = -(-(-(-height // 16) * 16 + 2 * halo) // (16 * world)) * 16 * world
+    plan = BandPlan(height, halo, rows_alloc, world)
+    owned = [plan.owned_rows(r) for r in range(world)]
+    covered = np.zeros(height, int)
+    for r, (y0, y1) in enumerate(owned):
+        covered[y0:y1] += 1
+        lo, hi = plan.padded_rows(r)
+        # every owned row's window of padded rows [y, y + 2*halo] lies inside chunk + halos
+        if y1 > y0:
+            assert y0 >= lo - halo and (y1 - 1) + 2 * halo <= hi + halo - 1
+            assert plan.cell_row_offset(r) >= 0
+            assert plan.cell_row_offset(r) + (-(-(y1 - y0) // 16) * 16) + 2 * halo <= plan.band_buffer_rows()
+    assert (covered == 1).all()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, height, halo, pitch, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rows_alloc = -(-(-(-height // 16) * 16 + 2 * halo) // (16 * world)) * 16 * world
+    plan = BandPlan(height, halo, rows_alloc, world)
+    images = [torch.from_numpy(np.random.default_rng(100 + r).integers(0, 9, (rows_alloc, pitch)).astype(np.float32))
+              for r in range(world)]
+    total = sum(images)
+    band = torch.full((plan.band_buffer_rows(), pitch), -1.0)
+    exchange_counts(images[rank], band, plan, rank, dist)
+    lo, hi = plan.padded_rows(rank)
+    ok = torch.equal(band[halo:halo + plan.chunk], total[lo:hi])
+    if halo:
+        above = total[lo - halo:lo] if rank > 0 else torch.zeros(halo, pitch)
+        below = total[hi:hi + halo] if rank < world - 1 else torch.zeros(halo, pitch)
+        ok = ok and torch.equal(band[:halo], above) and torch.equal(band[halo + plan.chunk:halo + plan.chunk + halo], below)
+    # what the composite pass would read for the rows this rank owns equals the global sum there
+    y0, y1 = plan.owned_rows(rank)
+    off = plan.cell_row_offset(rank)
+    if y1 > y0:
+        ok = ok and torch.equal(band[off:off + (y1 - y0) + 2 * halo], total[y0:y1 + 2 * halo])
+    out[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,height,halo", [(2, 64, 1), (2, 100, 3), (3, 96, 2), (2, 48, 0)])
+def test_exchange_counts_over_gloo(world, height, halo):
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_worker, args=(world, port, height, halo, 40, out), nprocs=world, join=True)
+        assert all(out[r] for r in range(world)), dict(out)
