@@ -11,20 +11,22 @@
 //   * warm-up frames with decay == 0 neither decay nor splat (:154);
 //   * trajectories never depend on the framebuffer.
 //
-// Layout in HBM (SoA, all sized npts unless noted):
+// Layout in HBM (SoA, all sized npts unless noted; DESIGN.md section 2):
 //   pos     float2   current positions            read + written every frame (streaming)
 //   orig    float2   positions to reset to        read only when a point resets (1/nframes of them)
-//   offset  uint32   reset phase of each point    read every frame (streaming)
-//   perm    uint32   original index of each slot  only for read_points
-//   vel     float2   (H, W) velocity field        random 8-byte gathers, kept L2-friendly by the sort
-//   hist    uint32   padded splat counters        one RED per point, read + cleared by the composite
+//   offset  u16/u32  reset phase of each point    read every frame (streaming); u16 if nframes <= 65536
+//   perm    uint32   original index of each slot  only for read_points and regrouping
+//   (a second copy of those four: regroup_points writes there and swaps)
+//   vel     float2   (H, W) velocity field        random 8-byte gathers
+//   hist    2 counter images (see CellMode)       one atomic per point, read + cleared by the composite
 //   img[2]  uint8    framebuffer (ping-pong only while a frame copy is in flight)
 //
-// Points are bucket-sorted ONCE at set-up by the image tile of their original position.  Neighbouring
-// points start together and, the field being smooth, travel together; resets send them home.  So a
-// warp's velocity gathers and counter updates stay within a few cache lines for the whole run
-// without any per-frame binning.  Results do not depend on the order (integer counts commute;
-// trajectories are per point); read_points undoes the permutation.
+// Points are kept in the order of the 8x4-texel tile they are in (counting sort at set-up, repeated
+// every nframes/16 frames: see regroup_points), so a warp's velocity gathers and counter updates stay
+// within a few cache lines.  Results do not depend on the order (integer counts commute; trajectories
+// are per point); read_points undoes the permutation.  Sparse clouds stay in the caller's order: their
+// cells carry the original point index (CELL_X64) so that the composite pass can keep the reference's
+// hit order.
 #include "device_utils.cuh"
 #include "internal.h"
 
@@ -112,23 +114,21 @@ __device__ __forceinline__ void cell_add_sat_u8(uint32_t* __restrict__ words, lo
     }
 }
 
-template <bool WRAP, int MODE, typename OffT>
-__global__ void __launch_bounds__(ADVECT_THREADS)
-advect_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
-              const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
-              uint32_t width, uint32_t height, float step, uint32_t phase, GeomDev g,
-              uint32_t* __restrict__ hist, uint32_t cap, int keep_cells) {
-    // A CTA owns ADVECT_THREADS * ADVECT_PTS consecutive points; thread t takes t, t + 256, t + 512, ...
-    // so every warp-wide access covers 32 CONSECUTIVE points: position / offset traffic is perfectly
-    // coalesced and, the points being stored in tile order, a warp's gather touches only a few lines.
-    // All loads of a phase are issued before the first use (the kernel is bound by memory latency:
-    // position -> texel -> counter is a dependent chain, so parallelism has to come from the points).
-    const uint32_t base = blockIdx.x * (ADVECT_THREADS * ADVECT_PTS) + threadIdx.x;
+// Euler step + reset of this thread's ADVECT_PTS points (advect_points.cc:144-153,163-171); returns
+// the new positions in p[] and which of them exist in live[].
+//
+// A CTA owns ADVECT_THREADS * ADVECT_PTS consecutive points; thread t takes t, t + 256, t + 512, ...
+// so every warp-wide access covers 32 CONSECUTIVE points: position / offset traffic is perfectly
+// coalesced and, the points being stored in tile order, a warp's gather touches only a few lines.
+// All loads of a phase are issued before the first use.
+template <bool WRAP, typename OffT>
+__device__ __forceinline__ void advance_points(float2* __restrict__ pos, const float2* __restrict__ orig,
+                                               const OffT* __restrict__ offset, uint32_t npts,
+                                               const float2* __restrict__ vel, uint32_t width, uint32_t height,
+                                               float step, uint32_t phase, uint32_t base,
+                                               float2 (&p)[ADVECT_PTS], bool (&live)[ADVECT_PTS]) {
     const uint64_t pol = make_stream_policy();
-    const uint64_t keep = keep_cells ? make_keep_policy() : make_normal_policy();
-    float2 p[ADVECT_PTS];
     uint32_t off[ADVECT_PTS];
-    bool live[ADVECT_PTS]; // no early return: the byte-cell update below is warp-collective
 #pragma unroll
     for (int k = 0; k < ADVECT_PTS; ++k) {
         const uint32_t i = base + k * ADVECT_THREADS;
@@ -158,6 +158,19 @@ advect_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
         if (off[k] == phase) p[k] = orig[i]; // reset AFTER the move (:147-152,166-170)
         if (live[k]) st_stream_f2(pos + i, p[k], pol);
     }
+}
+
+template <bool WRAP, int MODE, typename OffT>
+__global__ void __launch_bounds__(ADVECT_THREADS)
+advect_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
+              const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
+              uint32_t width, uint32_t height, float step, uint32_t phase, GeomDev g,
+              uint32_t* __restrict__ hist, uint32_t cap, int keep_cells) {
+    const uint32_t base = blockIdx.x * (ADVECT_THREADS * ADVECT_PTS) + threadIdx.x;
+    const uint64_t keep = keep_cells ? make_keep_policy() : make_normal_policy();
+    float2 p[ADVECT_PTS];
+    bool live[ADVECT_PTS]; // no early return: the byte-cell update below is warp-collective
+    advance_points<WRAP, OffT>(pos, orig, offset, npts, vel, width, height, step, phase, base, p, live);
     if (MODE != CELL_NONE) {
 #pragma unroll
         for (int k = 0; k < ADVECT_PTS; ++k) {
@@ -172,6 +185,93 @@ advect_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
             else if (MODE == CELL_F16) { if (at >= 0) cell_add_f16(hist, at, keep); }
             else cell_add_sat_u8(hist, at, cap);
         }
+    }
+}
+
+// ---- multi-GPU: the splat exchange fused into the advect kernel ------------------------------------
+//
+// With G GPUs the counter image is distributed by bands of `chunk` padded rows (band d on GPU d) and
+// never exists as a whole.  Each GPU advects ITS points and, instead of counting them locally and
+// summing dense images afterwards (67 MB per frame at 8192x4096), writes each point's cell -- one
+// 4-byte index into the OWNER's band buffer -- straight into the owner's inbox through peer-mapped
+// memory (NVLink / NVSwitch stores issued from inside the kernel).  A point whose row lies within
+// `halo` rows of a band edge is also sent to the neighbouring band, whose composite needs it, so no
+// separate halo exchange is left.  Slots are claimed per destination with one atomic per warp and
+// destination; the per-destination totals are what the ranks all-gather as the frame fence.
+constexpr int ROUTE_MAX_WORLD = 8;
+
+struct RouteDev {
+    int me, world;
+    int chunk, halo, pitch;             // band geometry in padded rows / cells
+    uint32_t capacity;                  // entries per (source, destination) segment
+    uint32_t* counts;                   // [world] entries sent to each destination this frame (local)
+    uint32_t* inbox[ROUTE_MAX_WORLD];   // this frame's inbox of every rank (peer-mapped), [world][capacity]
+};
+
+// Appends `entry` to the segment of destination `dst` (all 32 lanes call; dst < 0: nothing to send).
+__device__ __forceinline__ void route_send(const RouteDev& rt, int dst, uint32_t entry) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (int d = 0; d < rt.world; ++d) {
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, dst == d);
+        if (mask == 0u) continue;
+        uint32_t first = 0u;
+        const int leader = __ffs(mask) - 1;
+        if ((int)lane == leader) first = atomicAdd(rt.counts + d, (uint32_t)__popc(mask));
+        first = __shfl_sync(0xFFFFFFFFu, first, leader);
+        if (dst == d) {
+            const uint32_t slot = first + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+            if (slot < rt.capacity) rt.inbox[d][(size_t)rt.me * rt.capacity + slot] = entry;
+        }
+    }
+}
+
+template <bool WRAP, bool SPLAT, typename OffT>
+__global__ void __launch_bounds__(ADVECT_THREADS)
+advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
+                    const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
+                    uint32_t width, uint32_t height, float step, uint32_t phase, GeomDev g, RouteDev rt) {
+    const uint32_t base = blockIdx.x * (ADVECT_THREADS * ADVECT_PTS) + threadIdx.x;
+    float2 p[ADVECT_PTS];
+    bool live[ADVECT_PTS];
+    advance_points<WRAP, OffT>(pos, orig, offset, npts, vel, width, height, step, phase, base, p, live);
+    if (!SPLAT) return;
+#pragma unroll
+    for (int k = 0; k < ADVECT_PTS; ++k) {
+        const long long at = live[k] ? hist_index<WRAP>(f2i32_x86(p[k].x), f2i32_x86(p[k].y), g) : -1;
+        int owner = -1, up = -1, down = -1;
+        uint32_t e_own = 0u, e_up = 0u, e_down = 0u;
+        if (at >= 0) {
+            const int prow = (int)(at / g.pitch), col = (int)(at - (long long)prow * g.pitch);
+            owner = min(prow / rt.chunk, rt.world - 1);
+            const int r = prow - owner * rt.chunk; // row inside the owner's chunk
+            // band buffer rows: [halo above | chunk | halo below]
+            e_own = (uint32_t)((r + rt.halo) * rt.pitch + col);
+            if (r < rt.halo && owner > 0) { up = owner - 1; e_up = (uint32_t)((r + rt.chunk + rt.halo) * rt.pitch + col); }
+            if (r >= rt.chunk - rt.halo && owner < rt.world - 1) { down = owner + 1; e_down = (uint32_t)((r - rt.chunk + rt.halo) * rt.pitch + col); }
+        }
+        route_send(rt, owner, e_own);
+        if (rt.halo > 0) { // warp-uniform
+            route_send(rt, up, e_up);
+            route_send(rt, down, e_down);
+        }
+    }
+}
+
+// Counts the entries the other ranks (and this one) sent into this rank's band buffer.
+// counts_all[s * world + me] = number of entries from rank s.  CELLS: CELL_F16 or CELL_U32.
+template <int CELLS>
+__global__ void __launch_bounds__(256)
+drain_inbox_kernel(const uint32_t* __restrict__ inbox, uint32_t capacity, const uint32_t* __restrict__ counts_all,
+                   int me, int world, uint32_t* __restrict__ band, uint32_t band_cells) {
+    const int s = blockIdx.y;
+    const uint32_t n = min(counts_all[s * world + me], capacity);
+    const uint32_t* seg = inbox + (size_t)s * capacity;
+    const uint64_t keep = make_normal_policy();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t e = __ldcs(seg + i);
+        if (e >= band_cells) continue;
+        if (CELLS == CELL_F16) cell_add_f16(band, (long long)e, keep);
+        else atomicAdd(band + e, 1u);
     }
 }
 
