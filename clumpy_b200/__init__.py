@@ -64,6 +64,15 @@ SIGNATURES = {
     "clumpy_cuda_advect_composite_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
     "clumpy_cuda_advect_finish_frame": (C.c_int, [C.c_void_p]),
     "clumpy_cuda_advect_image_dev": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "clumpy_cuda_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "clumpy_cuda_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "clumpy_cuda_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "clumpy_cuda_advect_route_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint32,
+                                                 C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "clumpy_cuda_advect_route_peers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "clumpy_cuda_advect_route": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "clumpy_cuda_advect_drain": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "clumpy_cuda_advect_owned_rows": (C.c_int, [C.c_void_p, _u32p, _u32p]),
     "clumpy_cuda_advect_simframe": (C.c_int, [C.c_void_p, _u32p]),
     "clumpy_cuda_advect_frame_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "clumpy_cuda_advect_wait_frames": (C.c_int, [C.c_void_p]),
@@ -166,6 +175,20 @@ class Context:
         ms = C.c_float()
         _check(lib().clumpy_cuda_timer_stop(self._h, C.byref(ms)))
         return ms.value
+
+    def ipc_export(self, dptr):
+        """64-byte CUDA IPC handle of a device allocation (bytes), to hand to another process."""
+        buf = C.create_string_buffer(64)
+        _check(lib().clumpy_cuda_ipc_export(self._h, C.c_void_p(int(dptr)), buf))
+        return buf.raw
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        _check(lib().clumpy_cuda_ipc_open(self._h, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, dptr):
+        _check(lib().clumpy_cuda_ipc_close(self._h, C.c_void_p(int(dptr))))
 
     def launch_count(self):
         n = C.c_uint64()
@@ -307,6 +330,32 @@ class Advect:
 
     def finish_frame(self):
         _check(lib().clumpy_cuda_advect_finish_frame(self._h))
+
+    # ---- exchange fused into the advect kernel (peer-memory inboxes) ----------------------------
+
+    def route_begin(self, rank, world, capacity):
+        """-> (device address, bytes) of this rank's inbox allocation."""
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(lib().clumpy_cuda_advect_route_begin(self._h, rank, world, capacity, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def route_peers(self, inbox_ptrs):
+        arr = (C.c_void_p * len(inbox_ptrs))(*[C.c_void_p(int(p) if p else 0) for p in inbox_ptrs])
+        _check(lib().clumpy_cuda_advect_route_peers(self._h, arr))
+
+    def route(self):
+        """Advect + route this frame; -> device address of the world per-destination counts."""
+        p = C.c_void_p()
+        _check(lib().clumpy_cuda_advect_route(self._h, C.byref(p)))
+        return p.value
+
+    def drain(self, counts_all_dev):
+        _check(lib().clumpy_cuda_advect_drain(self._h, _vp(counts_all_dev)))
+
+    def owned_rows(self):
+        r0, n = C.c_uint32(), C.c_uint32()
+        _check(lib().clumpy_cuda_advect_owned_rows(self._h, C.byref(r0), C.byref(n)))
+        return r0.value, r0.value + n.value
 
     def image_dev(self):
         p = C.c_void_p()

@@ -32,6 +32,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <random>
 #include <vector>
 
@@ -208,22 +209,10 @@ struct RouteDev {
     uint32_t* inbox[ROUTE_MAX_WORLD];   // this frame's inbox of every rank (peer-mapped), [world][capacity]
 };
 
-// Appends `entry` to the segment of destination `dst` (all 32 lanes call; dst < 0: nothing to send).
-__device__ __forceinline__ void route_send(const RouteDev& rt, int dst, uint32_t entry) {
-    const uint32_t lane = threadIdx.x & 31u;
-    for (int d = 0; d < rt.world; ++d) {
-        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, dst == d);
-        if (mask == 0u) continue;
-        uint32_t first = 0u;
-        const int leader = __ffs(mask) - 1;
-        if ((int)lane == leader) first = atomicAdd(rt.counts + d, (uint32_t)__popc(mask));
-        first = __shfl_sync(0xFFFFFFFFu, first, leader);
-        if (dst == d) {
-            const uint32_t slot = first + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-            if (slot < rt.capacity) rt.inbox[d][(size_t)rt.me * rt.capacity + slot] = entry;
-        }
-    }
-}
+// Slot bookkeeping is hierarchical so that the per-destination totals are not hot atomics: lanes are
+// ranked inside their warp by ballot, warps claim a range of the CTA's count in shared memory, and the
+// CTA claims its range of the destination's segment with ONE global atomic per destination.
+constexpr int ROUTE_SENDS = ADVECT_PTS * 3; // per thread: owner + up to two neighbouring bands, per point
 
 template <bool WRAP, bool SPLAT, typename OffT>
 __global__ void __launch_bounds__(ADVECT_THREADS)
@@ -235,25 +224,54 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
     bool live[ADVECT_PTS];
     advance_points<WRAP, OffT>(pos, orig, offset, npts, vel, width, height, step, phase, base, p, live);
     if (!SPLAT) return;
+
+    __shared__ uint32_t cta_count[ROUTE_MAX_WORLD]; // entries of this CTA per destination, then its base
+    if (threadIdx.x < ROUTE_MAX_WORLD) cta_count[threadIdx.x] = 0u;
+    __syncthreads();
+
+    // what this thread sends: destination, entry (index into the destination's band buffer:
+    // rows [halo above | chunk | halo below]), and its rank among the CTA's entries for that destination
+    int dst[ROUTE_SENDS];
+    uint32_t entry[ROUTE_SENDS], local[ROUTE_SENDS];
+    const uint32_t lane = threadIdx.x & 31u;
 #pragma unroll
     for (int k = 0; k < ADVECT_PTS; ++k) {
         const long long at = live[k] ? hist_index<WRAP>(f2i32_x86(p[k].x), f2i32_x86(p[k].y), g) : -1;
-        int owner = -1, up = -1, down = -1;
-        uint32_t e_own = 0u, e_up = 0u, e_down = 0u;
+        dst[3 * k] = dst[3 * k + 1] = dst[3 * k + 2] = -1;
+        entry[3 * k] = entry[3 * k + 1] = entry[3 * k + 2] = 0u;
         if (at >= 0) {
             const int prow = (int)(at / g.pitch), col = (int)(at - (long long)prow * g.pitch);
-            owner = min(prow / rt.chunk, rt.world - 1);
+            const int owner = min(prow / rt.chunk, rt.world - 1);
             const int r = prow - owner * rt.chunk; // row inside the owner's chunk
-            // band buffer rows: [halo above | chunk | halo below]
-            e_own = (uint32_t)((r + rt.halo) * rt.pitch + col);
-            if (r < rt.halo && owner > 0) { up = owner - 1; e_up = (uint32_t)((r + rt.chunk + rt.halo) * rt.pitch + col); }
-            if (r >= rt.chunk - rt.halo && owner < rt.world - 1) { down = owner + 1; e_down = (uint32_t)((r - rt.chunk + rt.halo) * rt.pitch + col); }
+            dst[3 * k] = owner;
+            entry[3 * k] = (uint32_t)((r + rt.halo) * rt.pitch + col);
+            if (r < rt.halo && owner > 0) { dst[3 * k + 1] = owner - 1; entry[3 * k + 1] = (uint32_t)((r + rt.chunk + rt.halo) * rt.pitch + col); }
+            if (r >= rt.chunk - rt.halo && owner < rt.world - 1) { dst[3 * k + 2] = owner + 1; entry[3 * k + 2] = (uint32_t)((r - rt.chunk + rt.halo) * rt.pitch + col); }
         }
-        route_send(rt, owner, e_own);
-        if (rt.halo > 0) { // warp-uniform
-            route_send(rt, up, e_up);
-            route_send(rt, down, e_down);
-        }
+    }
+#pragma unroll
+    for (int j = 0; j < ROUTE_SENDS; ++j) {
+        local[j] = 0u;
+        if (!__any_sync(0xFFFFFFFFu, dst[j] >= 0)) continue; // typical for the neighbour-band sends
+        // lanes with the same destination form a group; idle lanes get keys of their own
+        const uint32_t mask = __match_any_sync(0xFFFFFFFFu, dst[j] >= 0 ? dst[j] : -1 - (int)lane);
+        const int leader = __ffs(mask) - 1;
+        uint32_t first = 0u;
+        if ((int)lane == leader && dst[j] >= 0) first = atomicAdd(&cta_count[dst[j]], (uint32_t)__popc(mask));
+        first = __shfl_sync(0xFFFFFFFFu, first, leader);
+        local[j] = first + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < rt.world) {
+        const uint32_t n = cta_count[threadIdx.x];
+        cta_count[threadIdx.x] = n ? atomicAdd(rt.counts + threadIdx.x, n) : 0u; // the CTA's base slot
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ROUTE_SENDS; ++j) {
+        if (dst[j] < 0) continue;
+        const uint32_t slot = cta_count[dst[j]] + local[j];
+        if (slot < rt.capacity) rt.inbox[dst[j]][(size_t)rt.me * rt.capacity + slot] = entry[j];
     }
 }
 
@@ -440,6 +458,18 @@ struct clumpy_advect {
     bool overlap = false, side_dirty = false;
     bool keep_cells = false;  // half-float counters are accessed with L2 evict-last hints
     bool count_open = false;  // advect_count was called, advect_finish_frame not yet
+    // multi-GPU routing (clumpy_cuda_advect_route_*): this rank's inbox, band buffer and peers
+    struct Route {
+        bool on = false;
+        int rank = 0, world = 1, chunk = 0;
+        uint32_t capacity = 0;
+        uint32_t* inbox = nullptr;   // [2 parities][world sources][capacity] cell indices
+        uint32_t* counts = nullptr;  // [2 parities][world destinations] entries sent this frame
+        uint32_t* band = nullptr;    // [halo | chunk | halo | slack] rows of counter cells
+        size_t band_bytes = 0;
+        uint32_t band_cells = 0;
+        uint32_t* peer_inbox[ROUTE_MAX_WORLD] = {nullptr};
+    } route;
     bool clear_pending[2] = {false, false};
     cudaEvent_t advected[2] = {nullptr, nullptr}, cleared[2] = {nullptr, nullptr}, side_done = nullptr;
     DenseTables dense;        // replay tables of the byte-counter path
@@ -463,6 +493,7 @@ static void advect_release(clumpy_advect* a) {
     cudaFree(a->pos); cudaFree(a->orig); cudaFree(a->vel); cudaFree(a->offset); cudaFree(a->perm);
     cudaFree(a->pos_alt); cudaFree(a->orig_alt); cudaFree(a->offset_alt); cudaFree(a->perm_alt);
     cudaFree(a->sort_counts); cudaFree(a->sort_sums);
+    cudaFree(a->route.inbox); cudaFree(a->route.counts); cudaFree(a->route.band);
     cudaFree(a->hist); cudaFree(a->img[0]); cudaFree(a->img[1]);
     free_dense_tables(&a->dense);
     for (int b = 0; b < 2; ++b) {
@@ -927,6 +958,152 @@ CLUMPY_API int clumpy_cuda_advect_composite_rows(clumpy_advect* adv, const void*
     if (adv->cell_mode == CELL_F16) return launch_composite_half(ctx, g, adv->dense, cells_dev, adv->wrapx, img, img);
     if (adv->cell_mode == CELL_X64) return launch_composite_exact(ctx, g, adv->rings, cells_dev, adv->wrapx, 1, adv->decay, img, img);
     return launch_composite(ctx, g, adv->rings, reinterpret_cast<const uint32_t*>(cells_dev), adv->wrapx, 1, adv->decay, img, img);
+}
+
+// ---- multi-GPU, fused exchange: points routed to the band owners through peer memory -------------
+
+CLUMPY_API int clumpy_cuda_ipc_export(clumpy_cuda_ctx* ctx, const void* dptr, void* handle64) {
+    REQUIRE(ctx && dptr && handle64, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == CLUMPY_IPC_HANDLE_BYTES, "IPC handle size");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, const_cast<void*>(dptr)));
+    memcpy(handle64, &h, sizeof(h));
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_ipc_open(clumpy_cuda_ctx* ctx, const void* handle64, void** dptr) {
+    REQUIRE(ctx && dptr && handle64, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    CK(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_ipc_close(clumpy_cuda_ctx* ctx, void* dptr) {
+    REQUIRE(ctx, "ctx is NULL");
+    CK(cudaSetDevice(ctx->device));
+    if (dptr) CK(cudaIpcCloseMemHandle(dptr));
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int world, uint32_t capacity,
+                                              void** inbox_dev, size_t* inbox_bytes) {
+    REQUIRE(adv && inbox_dev && inbox_bytes, "null argument");
+    REQUIRE(world >= 1 && world <= ROUTE_MAX_WORLD && rank >= 0 && rank < world, "bad rank / world size");
+    REQUIRE(adv->cell_mode == CELL_F16 || adv->cell_mode == CELL_U32, "routing needs count-only cells (f16 or u32)");
+    REQUIRE(adv->geom.rows % world == 0, "counter rows must be a multiple of the world size (CLUMPY_CUDA_CELL_ROWS_MULTIPLE)");
+    REQUIRE(capacity >= adv->npts, "capacity must be at least the largest shard");
+    REQUIRE(!adv->route.on, "routing already set up");
+    clumpy_cuda_ctx* ctx = adv->ctx;
+    CK(cudaSetDevice(ctx->device));
+    auto& rt = adv->route;
+    rt.rank = rank; rt.world = world; rt.capacity = std::max<uint32_t>(capacity, 1u);
+    rt.chunk = adv->geom.rows / world;
+    REQUIRE(world == 1 || rt.chunk >= 2 * adv->geom.halo, "bands thinner than the sprite are not supported");
+    const size_t cell_bytes = adv->cell_mode == CELL_F16 ? 2 : 4;
+    const size_t band_rows = (size_t)rt.chunk + 2 * adv->geom.halo + 32;
+    rt.band_cells = (uint32_t)(band_rows * adv->geom.pitch);
+    rt.band_bytes = round_up((size_t)rt.band_cells * cell_bytes, 256);
+    const size_t ibytes = 2ull * world * rt.capacity * sizeof(uint32_t);
+    CK(cudaMalloc(&rt.inbox, ibytes));
+    CK(cudaMalloc(&rt.counts, 2ull * world * sizeof(uint32_t)));
+    CK(cudaMalloc(&rt.band, rt.band_bytes));
+    CK(cudaMemsetAsync(rt.counts, 0, 2ull * world * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(rt.band, 0, rt.band_bytes, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    rt.peer_inbox[rank] = rt.inbox;
+    rt.on = true;
+    *inbox_dev = rt.inbox;
+    *inbox_bytes = ibytes;
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_advect_route_peers(clumpy_advect* adv, void* const* peer_inbox) {
+    REQUIRE(adv && peer_inbox && adv->route.on, "routing is not set up");
+    for (int r = 0; r < adv->route.world; ++r)
+        adv->route.peer_inbox[r] = (r == adv->route.rank) ? adv->route.inbox : static_cast<uint32_t*>(peer_inbox[r]);
+    for (int r = 0; r < adv->route.world; ++r) REQUIRE(adv->route.peer_inbox[r], "missing peer inbox");
+    return CLUMPY_OK;
+}
+
+template <bool WRAP, bool SPLAT, typename OffT>
+static void launch_route_t(clumpy_advect* a, uint32_t phase, const RouteDev& rd) {
+    const uint32_t grid = ceil_div(a->npts, ADVECT_THREADS * ADVECT_PTS);
+    const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch};
+    advect_route_kernel<WRAP, SPLAT, OffT><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
+        a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase, g, rd);
+}
+
+CLUMPY_API int clumpy_cuda_advect_route(clumpy_advect* adv, void** counts_dev) {
+    REQUIRE(adv && adv->route.on, "routing is not set up");
+    REQUIRE(!adv->count_open, "advect_route called twice without advect_drain");
+    clumpy_cuda_ctx* ctx = adv->ctx;
+    CK(cudaSetDevice(ctx->device));
+    auto& rt = adv->route;
+    const int parity = (int)(adv->simframe & 1u);
+    RouteDev rd;
+    rd.me = rt.rank; rd.world = rt.world; rd.chunk = rt.chunk; rd.halo = adv->geom.halo; rd.pitch = adv->geom.pitch;
+    rd.capacity = rt.capacity;
+    rd.counts = rt.counts + (size_t)parity * rt.world;
+    for (int r = 0; r < ROUTE_MAX_WORLD; ++r)
+        rd.inbox[r] = r < rt.world ? rt.peer_inbox[r] + (size_t)parity * rt.world * rt.capacity : nullptr;
+    CK(cudaMemsetAsync(rd.counts, 0, rt.world * sizeof(uint32_t), ctx->stream));
+    if (adv->npts) {
+        const bool splat = frame_splats(adv);
+        const uint32_t phase = adv->simframe % adv->nframes;
+#define ROUTE_LAUNCH(W, S) (adv->off16 ? launch_route_t<W, S, uint16_t>(adv, phase, rd) : launch_route_t<W, S, uint32_t>(adv, phase, rd))
+        if (adv->wrapx) { if (splat) ROUTE_LAUNCH(true, true); else ROUTE_LAUNCH(true, false); }
+        else            { if (splat) ROUTE_LAUNCH(false, true); else ROUTE_LAUNCH(false, false); }
+#undef ROUTE_LAUNCH
+        CK_LAUNCH(ctx);
+    }
+    adv->count_open = true;
+    if (counts_dev) *counts_dev = rd.counts;
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_advect_drain(clumpy_advect* adv, const uint32_t* counts_all_dev) {
+    REQUIRE(adv && adv->route.on && counts_all_dev, "routing is not set up");
+    REQUIRE(adv->count_open, "advect_drain without advect_route");
+    clumpy_cuda_ctx* ctx = adv->ctx;
+    CK(cudaSetDevice(ctx->device));
+    auto& rt = adv->route;
+    const int h = adv->geom.halo;
+    if (frame_splats(adv)) {
+        const int parity = (int)(adv->simframe & 1u);
+        const uint32_t* inbox = rt.inbox + (size_t)parity * rt.world * rt.capacity;
+        const dim3 grid(std::min<uint32_t>(ceil_div(rt.capacity, 256), (uint32_t)ctx->sm_count * 2), rt.world);
+        if (adv->cell_mode == CELL_F16)
+            drain_inbox_kernel<CELL_F16><<<grid, 256, 0, ctx->stream>>>(inbox, rt.capacity, counts_all_dev, rt.rank, rt.world, rt.band, rt.band_cells);
+        else
+            drain_inbox_kernel<CELL_U32><<<grid, 256, 0, ctx->stream>>>(inbox, rt.capacity, counts_all_dev, rt.rank, rt.world, rt.band, rt.band_cells);
+        CK_LAUNCH(ctx);
+        // image rows this rank owns: those whose window of padded rows lies in chunk + halos
+        const int lo = rt.rank * rt.chunk;
+        const int y0 = std::max(0, lo - h), y1 = std::min((int)adv->height, lo + rt.chunk - h);
+        if (y1 > y0) {
+            const size_t cell_bytes = adv->cell_mode == CELL_F16 ? 2 : 4;
+            const char* cells = reinterpret_cast<const char*>(rt.band) + (size_t)(y0 - (lo - h)) * adv->geom.pitch * cell_bytes;
+            int rc = clumpy_cuda_advect_composite_rows(adv, cells, (uint32_t)y0, (uint32_t)(y1 - y0));
+            if (rc) return rc;
+        }
+        CK(cudaMemsetAsync(rt.band, 0, rt.band_bytes, ctx->stream));
+    }
+    adv->count_open = false;
+    adv->simframe += 1;
+    if (adv->regroup_every && ++adv->frames_since_regroup >= adv->regroup_every) return regroup_points(adv);
+    return CLUMPY_OK;
+}
+
+CLUMPY_API int clumpy_cuda_advect_owned_rows(clumpy_advect* adv, uint32_t* row0, uint32_t* nrows) {
+    REQUIRE(adv && row0 && nrows && adv->route.on, "routing is not set up");
+    const int h = adv->geom.halo, lo = adv->route.rank * adv->route.chunk;
+    const int y0 = std::max(0, lo - h), y1 = std::min((int)adv->height, lo + adv->route.chunk - h);
+    *row0 = (uint32_t)y0;
+    *nrows = (uint32_t)std::max(0, y1 - y0);
+    return CLUMPY_OK;
 }
 
 CLUMPY_API int clumpy_cuda_advect_image_dev(clumpy_advect* adv, void** img_dev) {

@@ -180,6 +180,83 @@ class ShardedAdvect:
         self.adv.close()
 
 
+class RoutedAdvect:
+    """advect_points across ranks with the splat exchange FUSED into the advect kernel: the counter
+    image is distributed by row bands and every rank's advect kernel stores each point's cell index
+    straight into the owning rank's inbox through peer-mapped memory (CUDA IPC over NVLink); see
+    include/clumpy_cuda.h "multi-GPU with the exchange fused into the advect kernel".  Per frame the
+    only collective is an all-gather of world x world entry counts, which is also the frame fence."""
+
+    def __init__(self, ctx, pts, vel, step_size, kernel_size, decay, nframes, dist, device):
+        import torch
+        import clumpy_b200
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.ctx, self.device = ctx, device
+        self.h_img, self.w_img = vel.shape[:2]
+        n = self.n_total = len(pts)
+        lo, hi = shard_range(n, self.world, self.rank)
+        offsets = clumpy_b200.age_offsets(nframes, n)[lo:hi]
+        os.environ["CLUMPY_CUDA_CELLS"] = "f16" if kernel_size <= 3 else "u32"
+        os.environ["CLUMPY_CUDA_OVERLAP"] = "0"
+        os.environ["CLUMPY_CUDA_CELL_ROWS_MULTIPLE"] = str(CELL_ROW_MULTIPLE * self.world)
+        self.adv = ctx.advect(np.ascontiguousarray(pts[lo:hi]), vel, step_size, kernel_size, decay, nframes,
+                              age_offset=offsets)
+        capacity = max(shard_range(n, self.world, r)[1] - shard_range(n, self.world, r)[0] for r in range(self.world))
+        inbox, _ = self.adv.route_begin(self.rank, self.world, capacity)
+        # exchange CUDA IPC handles of the inboxes and map the peers'
+        handles = [None] * self.world
+        dist.all_gather_object(handles, ctx.ipc_export(inbox))
+        self.peer_ptrs = [inbox if r == self.rank else ctx.ipc_open(handles[r]) for r in range(self.world)]
+        self.adv.route_peers(self.peer_ptrs)
+        self.counts_all = torch.zeros((self.world, self.world), dtype=torch.int32, device=device)
+        self.y0, self.y1 = self.adv.owned_rows()
+        self._counts_view = {}
+        dist.barrier()
+
+    def step(self, count=1):
+        torch, dist = self.torch, self.dist
+        for _ in range(count):
+            ptr = self.adv.route()
+            mine = self._counts_view.get(ptr)
+            if mine is None:
+                mine = torch.as_tensor(_DeviceView(ptr, (self.world,), "<i4"), device=self.device)
+                self._counts_view[ptr] = mine
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.counts_all, mine)  # also the frame fence
+            else:
+                self.counts_all[0].copy_(mine)
+            self.adv.drain(self.counts_all.data_ptr())
+
+    band_image = ShardedAdvect.band_image
+    gather_image = ShardedAdvect.gather_image
+
+    def points(self):
+        torch, dist = self.torch, self.dist
+        mine = torch.from_numpy(self.adv.points()).to(self.device)
+        if self.world == 1:
+            return mine.cpu().numpy()
+        parts = [torch.empty((hi - lo, 2), dtype=torch.float32, device=self.device)
+                 for lo, hi in (shard_range(self.n_total, self.world, r) for r in range(self.world))]
+        dist.all_gather(parts, mine)
+        return torch.cat(parts).cpu().numpy()
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()  # nobody may still be writing into an inbox that is about to go away
+        for r, p in enumerate(self.peer_ptrs):
+            if r != self.rank and p:
+                self.ctx.ipc_close(p)
+        self.adv.close()
+
+
+def make_sharded(kind, *a, **kw):
+    """kind: "routed" (exchange fused into the advect kernel, default) or "dense" (counter images
+    summed with an NCCL reduce-scatter)."""
+    return (RoutedAdvect if kind == "routed" else ShardedAdvect)(*a, **kw)
+
+
 def bench_multi(args, cfg, workload, metric, unit):
     """bench.py body for --gpus N > 1 (launched by torch.distributed.run, one rank per GPU)."""
     import torch
@@ -210,8 +287,9 @@ def bench_multi(args, cfg, workload, metric, unit):
     del d_pot, d_vel
     pts = synth_points(n, w, h)
 
-    run = ShardedAdvect(ctx, pts, vel.numpy(), cfg["step_size"], cfg["kernel_size"], cfg["decay"], cfg["nframes"],
-                        dist, device)
+    kind = os.environ.get("CLUMPY_MULTIGPU", "routed")
+    run = make_sharded(kind, ctx, pts, vel.numpy(), cfg["step_size"], cfg["kernel_size"], cfg["decay"], cfg["nframes"],
+                       dist, device)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     run.step(W)
     dist.barrier()
@@ -236,7 +314,7 @@ def bench_multi(args, cfg, workload, metric, unit):
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    run2 = ShardedAdvect(ctx, pts, vel.numpy(), cfg["step_size"], cfg["kernel_size"], cfg["decay"], nrec, dist, device)
+    run2 = make_sharded(kind, ctx, pts, vel.numpy(), cfg["step_size"], cfg["kernel_size"], cfg["decay"], nrec, dist, device)
     run2.step(nrec)
     for f in range(nrec):
         run2.step(1)
@@ -257,8 +335,12 @@ def bench_multi(args, cfg, workload, metric, unit):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32+u8", "data": "synthetic",
             "config": {"workload": workload, "frames_per_s": K / (ms * 1e-3),
-                       "parallelism": f"points sharded x{world}, field replicated, per-frame NCCL reduce-scatter of the "
-                                      "f16 counter image by row bands + halo all-gather, band composite per rank",
+                       "parallelism": (f"points sharded x{world}, field replicated, counter image distributed by row "
+                                       "bands; each advect kernel stores its points' cell indices into the band owners' "
+                                       "inboxes through peer memory (NVLink), all-gather of the entry counts as the "
+                                       "frame fence, band composite per rank") if kind == "routed" else
+                                      (f"points sharded x{world}, field replicated, per-frame NCCL reduce-scatter of the "
+                                       "f16 counter image by row bands + halo all-gather, band composite per rank"),
                        "l2": "inputs larger than L2 (field 268 MB per GPU)"},
             "clocks": clocks,
             "e2e": {"value": n * e2e_steps / dt, "unit": unit,

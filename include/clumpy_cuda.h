@@ -165,6 +165,34 @@ int clumpy_cuda_advect_composite_rows(clumpy_advect* adv, const void* cells_dev,
                                       uint32_t nrows);
 int clumpy_cuda_advect_finish_frame(clumpy_advect* adv);
 
+/* ---- multi-GPU with the exchange fused into the advect kernel -----------------------------------
+ * The counter image is distributed by bands of padded rows (band g on GPU g) and never exists as a
+ * whole.  clumpy_cuda_advect_route advects this GPU's points and stores each point's cell index
+ * (4 bytes) straight into the inbox of the GPU that owns the cell's band -- and of the neighbouring
+ * band when the row lies within the sprite's reach of the edge -- through peer-mapped memory
+ * (NVLink / NVSwitch stores from inside the kernel).  The per-destination entry counts it leaves in
+ * *counts_dev (world x uint32) are all-gathered by the caller (that collective is also the frame
+ * fence); clumpy_cuda_advect_drain then counts this GPU's inbox into its band buffer, composites the
+ * image rows it owns, clears the band and advances the frame.  Inboxes are double-buffered by frame
+ * parity, so a GPU may already route frame s+1 while a peer still drains frame s.
+ *
+ *   set-up:   route_begin (allocates this rank's inbox; export it with clumpy_cuda_ipc_export,
+ *             exchange the handles, open the peers' with clumpy_cuda_ipc_open) -> route_peers
+ *   a frame:  route -> all-gather(counts) -> drain(counts_all)        counts_all[s*world + d]
+ *
+ * `capacity` = entries per (source, destination) segment, at least the largest shard's point count.
+ * Needs count-only cells and CLUMPY_CUDA_CELL_ROWS_MULTIPLE = 16 * world at advect_begin. */
+#define CLUMPY_IPC_HANDLE_BYTES 64
+int clumpy_cuda_ipc_export(clumpy_cuda_ctx* ctx, const void* dptr, void* handle64);
+int clumpy_cuda_ipc_open(clumpy_cuda_ctx* ctx, const void* handle64, void** dptr);
+int clumpy_cuda_ipc_close(clumpy_cuda_ctx* ctx, void* dptr);
+int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int world, uint32_t capacity,
+                                   void** inbox_dev, size_t* inbox_bytes);
+int clumpy_cuda_advect_route_peers(clumpy_advect* adv, void* const* peer_inbox);
+int clumpy_cuda_advect_route(clumpy_advect* adv, void** counts_dev);
+int clumpy_cuda_advect_drain(clumpy_advect* adv, const uint32_t* counts_all_dev);
+int clumpy_cuda_advect_owned_rows(clumpy_advect* adv, uint32_t* row0, uint32_t* nrows);
+
 /* Device address of the current framebuffer (height * width u8), for callers that gather row
  * bands across GPUs themselves. */
 int clumpy_cuda_advect_image_dev(clumpy_advect* adv, void** img_dev);

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import clumpy_b200  # noqa: E402
 import oracle  # noqa: E402
-from clumpy_b200.multigpu import ShardedAdvect  # noqa: E402
+from clumpy_b200.multigpu import make_sharded  # noqa: E402
 
 
 def main():
@@ -30,29 +30,31 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = clumpy_b200.Context(local, stream.cuda_stream)
     ok = True
-    for (w, h, n, k, decay, nframes, step) in [(320, 200, 70001, 3, 0.98, 6, 35.0), (256, 160, 30000, 1, 0.9, 5, 40.0),
+    kinds = os.environ.get("CLUMPY_MULTIGPU_KINDS", "routed,dense").split(",")
+    for kind in kinds:
+      for (w, h, n, k, decay, nframes, step) in [(320, 200, 70001, 3, 0.98, 6, 35.0), (256, 160, 30000, 1, 0.9, 5, 40.0),
                                                (200, 136, 20000, 5, 0.95, 4, 30.0), (512, 64, 50000, 3, -0.97, 4, 60.0)]:
-        pot, _, _ = oracle.generate_simplex(w, h, 1.0, 5.0, 8)
-        vel, _, _ = oracle.curl_2d(pot)
-        pts = ((np.random.default_rng(21).random((n, 2)) * 1.04 - 0.02) * [w, h]).astype(np.float32)
-        run = ShardedAdvect(ctx, pts, vel, step, k, decay, nframes, dist, device)
-        ref = oracle.Advect(pts, vel, step, k, decay, nframes) if rank == 0 else None
-        for s in range(2 * nframes):
-            run.step()
-            img = run.gather_image()
-            traj = run.points()
-            if rank == 0:
-                ref.step()
-                d = np.abs(img.astype(int) - ref.image().astype(int))
-                frac = float((d <= 1).mean())
-                same = np.array_equal(traj.view(np.uint32), ref.points().view(np.uint32))
-                if frac < 0.999 or not same:
-                    ok = False
-                    print(f"MISMATCH {w}x{h} k={k} frame {s}: within1={frac:.5f} max={d.max()} traj_equal={same}")
-        if rank == 0:
-            print(f"case {w}x{h} n={n} k={k} decay={decay}: ok={ok} owned rows per rank: "
-                  f"{[run.plan.owned_rows(r) for r in range(run.world)]}")
-        run.close()
+          pot, _, _ = oracle.generate_simplex(w, h, 1.0, 5.0, 8)
+          vel, _, _ = oracle.curl_2d(pot)
+          pts = ((np.random.default_rng(21).random((n, 2)) * 1.04 - 0.02) * [w, h]).astype(np.float32)
+          run = make_sharded(kind, ctx, pts, vel, step, k, decay, nframes, dist, device)
+          ref = oracle.Advect(pts, vel, step, k, decay, nframes) if rank == 0 else None
+          for s in range(2 * nframes):
+              run.step()
+              img = run.gather_image()
+              traj = run.points()
+              if rank == 0:
+                  ref.step()
+                  d = np.abs(img.astype(int) - ref.image().astype(int))
+                  frac = float((d <= 1).mean())
+                  same = np.array_equal(traj.view(np.uint32), ref.points().view(np.uint32))
+                  if frac < 0.999 or not same:
+                      ok = False
+                      print(f"MISMATCH [{kind}] {w}x{h} k={k} frame {s}: within1={frac:.5f} max={d.max()} traj_equal={same}")
+          if rank == 0:
+              print(f"[{kind}] case {w}x{h} n={n} k={k} decay={decay}: ok={ok} owned rows per rank: "
+                    f"{(run.y0, run.y1)}")
+          run.close()
     flag = torch.tensor([0 if ok else 1], device=device)
     dist.all_reduce(flag)
     ctx.close()
