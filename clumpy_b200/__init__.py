@@ -73,6 +73,9 @@ SIGNATURES = {
     "clumpy_cuda_advect_route": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "clumpy_cuda_advect_drain": (C.c_int, [C.c_void_p, C.c_void_p]),
     "clumpy_cuda_advect_owned_rows": (C.c_int, [C.c_void_p, _u32p, _u32p]),
+    "clumpy_cuda_advect_route_steps": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "clumpy_cuda_advect_route_errors": (C.c_int, [C.c_void_p, _u32p]),
+    "clumpy_cuda_advect_route_profile": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _f32p, _f32p]),
     "clumpy_cuda_advect_simframe": (C.c_int, [C.c_void_p, _u32p]),
     "clumpy_cuda_advect_frame_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "clumpy_cuda_advect_wait_frames": (C.c_int, [C.c_void_p]),
@@ -351,6 +354,19 @@ class Advect:
 
     def drain(self, counts_all_dev):
         _check(lib().clumpy_cuda_advect_drain(self._h, _vp(counts_all_dev)))
+
+    def route_steps(self, count):
+        _check(lib().clumpy_cuda_advect_route_steps(self._h, count))
+
+    def route_profile(self, count):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        _check(lib().clumpy_cuda_advect_route_profile(self._h, count, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def route_errors(self):
+        n = C.c_uint32()
+        _check(lib().clumpy_cuda_advect_route_errors(self._h, C.byref(n)))
+        return n.value
 
     def owned_rows(self):
         r0, n = C.c_uint32(), C.c_uint32()

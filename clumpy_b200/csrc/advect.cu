@@ -126,9 +126,9 @@ template <bool WRAP, typename OffT>
 __device__ __forceinline__ void advance_points(float2* __restrict__ pos, const float2* __restrict__ orig,
                                                const OffT* __restrict__ offset, uint32_t npts,
                                                const float2* __restrict__ vel, uint32_t width, uint32_t height,
-                                               float step, uint32_t phase, uint32_t base,
+                                               float step, uint32_t phase, uint32_t base, bool stream_hint,
                                                float2 (&p)[ADVECT_PTS], bool (&live)[ADVECT_PTS]) {
-    const uint64_t pol = make_stream_policy();
+    const uint64_t pol = stream_hint ? make_stream_policy() : make_normal_policy();
     uint32_t off[ADVECT_PTS];
 #pragma unroll
     for (int k = 0; k < ADVECT_PTS; ++k) {
@@ -171,7 +171,7 @@ advect_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
     const uint64_t keep = keep_cells ? make_keep_policy() : make_normal_policy();
     float2 p[ADVECT_PTS];
     bool live[ADVECT_PTS]; // no early return: the byte-cell update below is warp-collective
-    advance_points<WRAP, OffT>(pos, orig, offset, npts, vel, width, height, step, phase, base, p, live);
+    advance_points<WRAP, OffT>(pos, orig, offset, npts, vel, width, height, step, phase, base, g.keep_pos == 0, p, live);
     if (MODE != CELL_NONE) {
 #pragma unroll
         for (int k = 0; k < ADVECT_PTS; ++k) {
@@ -193,103 +193,211 @@ advect_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
 //
 // With G GPUs the counter image is distributed by bands of `chunk` padded rows (band d on GPU d) and
 // never exists as a whole.  Each GPU advects ITS points and, instead of counting them locally and
-// summing dense images afterwards (67 MB per frame at 8192x4096), writes each point's cell -- one
-// 4-byte index into the OWNER's band buffer -- straight into the owner's inbox through peer-mapped
-// memory (NVLink / NVSwitch stores issued from inside the kernel).  A point whose row lies within
-// `halo` rows of a band edge is also sent to the neighbouring band, whose composite needs it, so no
-// separate halo exchange is left.  Slots are claimed per destination with one atomic per warp and
-// destination; the per-destination totals are what the ranks all-gather as the frame fence.
+// summing dense images afterwards (67 MB per frame at 8192x4096), counts the points that land in its
+// own band straight into its band buffer and writes every other point's cell -- one 4-byte index into
+// the OWNER's band buffer -- into the owner's inbox through peer-mapped memory (NVLink / NVSwitch
+// stores issued from inside the kernel).  A point whose row lies within `halo` rows of a band edge is
+// also sent to the neighbouring band, whose composite needs it, so no separate halo exchange is left.
+//
+// No global slot counters: CTA c of source rank s owns the fixed region [c * ROUTE_BLOCK,
+// (c + 1) * ROUTE_BLOCK) of segment s in every destination's inbox (a CTA advects ROUTE_BLOCK points and
+// a point sends at most one entry per destination), ranks its entries with a shared-memory atomic, and
+// leaves the number it wrote in the destination's count word [s][c].  The receiver reads the count
+// words, zeroes the ones it used, and counts the entries into its band.  The frame fence (an epoch
+// flag per source in the receiver's memory) is published by the last CTA of the kernel.
 constexpr int ROUTE_MAX_WORLD = 8;
+constexpr uint32_t ROUTE_BLOCK = ADVECT_THREADS * ADVECT_PTS; // points per CTA = entry slots per region
+constexpr int ROUTE_BANDS = 4;                                // band buffers in flight per rank
 
 struct RouteDev {
     int me, world;
     int chunk, halo, pitch;             // band geometry in padded rows / cells
-    uint32_t capacity;                  // entries per (source, destination) segment
-    uint32_t* counts;                   // [world] entries sent to each destination this frame (local)
-    uint32_t* inbox[ROUTE_MAX_WORLD];   // this frame's inbox of every rank (peer-mapped), [world][capacity]
+    uint32_t nregion;                   // regions (= CTAs of the largest shard) per source segment
+    uint32_t* inbox[ROUTE_MAX_WORLD];   // rank r's entries of this frame's parity (peer-mapped): [world][nregion * ROUTE_BLOCK]
+    uint32_t* cnt[ROUTE_MAX_WORLD];     // rank r's count words of this frame's parity (peer-mapped): [world][nregion]
+    uint32_t* flags[ROUTE_MAX_WORLD];   // rank r's epoch flags (peer-mapped): [world]
+    uint32_t* band;                     // this rank's band buffer (points landing in my own band count directly)
+    int band_f16;                       // band cells are half floats (else uint32)
+    int signal;                         // 1: the last CTA publishes the epoch; 0: the caller fences
+    int loopback;                       // profiling aid: every "peer" is this rank itself (see route_begin)
+    uint32_t epoch;
+    uint32_t* ticket;                   // CTAs done so far (reset by the last one)
 };
 
-// Slot bookkeeping is hierarchical so that the per-destination totals are not hot atomics: lanes are
-// ranked inside their warp by ballot, warps claim a range of the CTA's count in shared memory, and the
-// CTA claims its range of the destination's segment with ONE global atomic per destination.
-constexpr int ROUTE_SENDS = ADVECT_PTS * 3; // per thread: owner + up to two neighbouring bands, per point
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// flags[me] = epoch in rank d's memory.  Called after every store of the frame has been fenced.
+__device__ __forceinline__ void publish_frame(const RouteDev& rt, int d) {
+    const int slot = rt.loopback ? d : rt.me; // loopback: play every source of my own inbox
+    *reinterpret_cast<volatile uint32_t*>(rt.flags[d] + slot) = rt.epoch;
+}
+
+// One entry for rank `dst`: the CTA-wide rank comes from a shared-memory atomic, the slot is fixed by
+// the CTA's region, the store goes over NVLink.
+__device__ __forceinline__ void route_send(const RouteDev& rt, uint32_t* cta_n, int dst, uint32_t entry) {
+    const uint32_t r = atomicAdd(cta_n + dst, 1u);
+    rt.inbox[dst][((size_t)rt.me * rt.nregion + blockIdx.x) * ROUTE_BLOCK + r] = entry;
+}
+
+// A cell of padded row `r` (relative to band `owner`'s first row) and padded column `ux`: counted
+// straight into this rank's band buffer when it is ours, sent to the owner's inbox otherwise; rows
+// within the sprite's reach of a band edge also go to the neighbouring band, whose composite needs them.
+__device__ __forceinline__ void route_cell(const RouteDev& rt, uint32_t* cta_n, int owner, int r, uint32_t ux) {
+    const uint32_t entry = (uint32_t)((r + rt.halo) * rt.pitch) + ux; // band rows: [halo above | chunk | halo below]
+    if (owner == rt.me) {
+        if (rt.band_f16) cell_add_f16(rt.band, (long long)entry, make_normal_policy());
+        else atomicAdd(rt.band + entry, 1u);
+    } else {
+        route_send(rt, cta_n, owner, entry);
+    }
+    if (r < rt.halo && owner > 0) route_send(rt, cta_n, owner - 1, (uint32_t)((r + rt.chunk + rt.halo) * rt.pitch) + ux);
+    if (r >= rt.chunk - rt.halo && owner < rt.world - 1) route_send(rt, cta_n, owner + 1, (uint32_t)((r - rt.chunk + rt.halo) * rt.pitch) + ux);
+}
 
 template <bool WRAP, bool SPLAT, typename OffT>
 __global__ void __launch_bounds__(ADVECT_THREADS)
 advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                     const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
                     uint32_t width, uint32_t height, float step, uint32_t phase, GeomDev g, RouteDev rt) {
-    const uint32_t base = blockIdx.x * (ADVECT_THREADS * ADVECT_PTS) + threadIdx.x;
+    __shared__ uint32_t cta_n[ROUTE_MAX_WORLD]; // entries this CTA has written per destination
+    if (SPLAT) {
+        if (threadIdx.x < ROUTE_MAX_WORLD) cta_n[threadIdx.x] = 0u;
+        __syncthreads(); // here, where every warp arrives at once, not after the loads
+    }
+    const uint32_t base = blockIdx.x * ROUTE_BLOCK + threadIdx.x;
     float2 p[ADVECT_PTS];
     bool live[ADVECT_PTS];
-    advance_points<WRAP, OffT>(pos, orig, offset, npts, vel, width, height, step, phase, base, p, live);
+    advance_points<WRAP, OffT>(pos, orig, offset, npts, vel, width, height, step, phase, base, g.keep_pos == 0, p, live);
     if (!SPLAT) return;
 
-    __shared__ uint32_t cta_count[ROUTE_MAX_WORLD]; // entries of this CTA per destination, then its base
-    if (threadIdx.x < ROUTE_MAX_WORLD) cta_count[threadIdx.x] = 0u;
-    __syncthreads();
-
-    // what this thread sends: destination, entry (index into the destination's band buffer:
-    // rows [halo above | chunk | halo below]), and its rank among the CTA's entries for that destination
-    int dst[ROUTE_SENDS];
-    uint32_t entry[ROUTE_SENDS], local[ROUTE_SENDS];
-    const uint32_t lane = threadIdx.x & 31u;
+    const int my_lo = rt.me * rt.chunk; // first padded row of this rank's band
 #pragma unroll
     for (int k = 0; k < ADVECT_PTS; ++k) {
-        const long long at = live[k] ? hist_index<WRAP>(f2i32_x86(p[k].x), f2i32_x86(p[k].y), g) : -1;
-        dst[3 * k] = dst[3 * k + 1] = dst[3 * k + 2] = -1;
-        entry[3 * k] = entry[3 * k + 1] = entry[3 * k + 2] = 0u;
-        if (at >= 0) {
-            const int prow = (int)(at / g.pitch), col = (int)(at - (long long)prow * g.pitch);
-            const int owner = min(prow / rt.chunk, rt.world - 1);
-            const int r = prow - owner * rt.chunk; // row inside the owner's chunk
-            dst[3 * k] = owner;
-            entry[3 * k] = (uint32_t)((r + rt.halo) * rt.pitch + col);
-            if (r < rt.halo && owner > 0) { dst[3 * k + 1] = owner - 1; entry[3 * k + 1] = (uint32_t)((r + rt.chunk + rt.halo) * rt.pitch + col); }
-            if (r >= rt.chunk - rt.halo && owner < rt.world - 1) { dst[3 * k + 2] = owner + 1; entry[3 * k + 2] = (uint32_t)((r - rt.chunk + rt.halo) * rt.pitch + col); }
+        // splat_points.cc:143-144: centre texel by (int32_t) truncation; same tests as hist_index
+        const int32_t cx = f2i32_x86(p[k].x), cy = f2i32_x86(p[k].y);
+        const uint32_t uy = (uint32_t)cy + (uint32_t)g.halo;
+        uint32_t ux;
+        bool inside = live[k] && uy < (uint32_t)(g.height + 2 * g.halo);
+        if (WRAP) {
+            int32_t m = cx % g.width;
+            if (m < 0) m += g.width;
+            ux = (uint32_t)(m + g.halo);
+        } else {
+            ux = (uint32_t)cx + (uint32_t)g.halo;
+            inside = inside && ux < (uint32_t)(g.width + 2 * g.halo);
+        }
+        if (!inside) continue;
+        const int r = (int)uy - my_lo;
+        if ((uint32_t)r < (uint32_t)rt.chunk) {
+            route_cell(rt, cta_n, rt.me, r, ux);
+        } else {
+            const int owner = min((int)(uy / (uint32_t)rt.chunk), rt.world - 1);
+            route_cell(rt, cta_n, owner, (int)uy - owner * rt.chunk, ux);
         }
     }
-#pragma unroll
-    for (int j = 0; j < ROUTE_SENDS; ++j) {
-        local[j] = 0u;
-        if (!__any_sync(0xFFFFFFFFu, dst[j] >= 0)) continue; // typical for the neighbour-band sends
-        // lanes with the same destination form a group; idle lanes get keys of their own
-        const uint32_t mask = __match_any_sync(0xFFFFFFFFu, dst[j] >= 0 ? dst[j] : -1 - (int)lane);
-        const int leader = __ffs(mask) - 1;
-        uint32_t first = 0u;
-        if ((int)lane == leader && dst[j] >= 0) first = atomicAdd(&cta_count[dst[j]], (uint32_t)__popc(mask));
-        first = __shfl_sync(0xFFFFFFFFu, first, leader);
-        local[j] = first + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+    __syncthreads(); // all entries of this CTA are written, cta_n is final
+    if (threadIdx.x >= 32) return;
+    // Warp 0: leave the non-zero counts with their destinations (the receivers zero them again), then
+    // take part in the frame fence.  A CTA that stored into an inbox fences those stores at system scope
+    // (bar.sync / syncwarp order them before thread 0's cumulative fence.sys; CTAs whose points all
+    // landed in this rank's own band skip the fence, which costs microseconds) and then adds itself to
+    // the ticket with a fire-and-forget reduction.  The LAST CTA of the grid (dispatched last, so among
+    // the last to finish) waits until all the others have done so and publishes the frame's epoch to
+    // every peer: release = fence + ticket on the senders' side, acquire = ticket read + fence here.
+    const uint32_t n = (int)threadIdx.x < rt.world ? cta_n[threadIdx.x] : 0u;
+    if (n) *reinterpret_cast<volatile uint32_t*>(rt.cnt[threadIdx.x] + (size_t)rt.me * rt.nregion + blockIdx.x) = n;
+    const bool cta_sent = __any_sync(0xFFFFFFFFu, n != 0u);
+    if (!rt.signal) return;
+    if (threadIdx.x == 0 && cta_sent) __threadfence_system();
+    if (blockIdx.x != gridDim.x - 1u) {
+        if (threadIdx.x == 0) asm volatile("red.global.add.u32 [%0], 1;" :: "l"(rt.ticket) : "memory");
+        return;
     }
-    __syncthreads();
-    if ((int)threadIdx.x < rt.world) {
-        const uint32_t n = cta_count[threadIdx.x];
-        cta_count[threadIdx.x] = n ? atomicAdd(rt.counts + threadIdx.x, n) : 0u; // the CTA's base slot
+    if (threadIdx.x == 0) {
+        const volatile uint32_t* t = rt.ticket;
+        while (*t != gridDim.x - 1u) __nanosleep(40);
+        *rt.ticket = 0u;
+        __threadfence_system();
     }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < ROUTE_SENDS; ++j) {
-        if (dst[j] < 0) continue;
-        const uint32_t slot = cta_count[dst[j]] + local[j];
-        if (slot < rt.capacity) rt.inbox[dst[j]][(size_t)rt.me * rt.capacity + slot] = entry[j];
-    }
+    __syncwarp();
+    if ((int)threadIdx.x < rt.world) publish_frame(rt, (int)threadIdx.x);
 }
 
-// Counts the entries the other ranks (and this one) sent into this rank's band buffer.
-// counts_all[s * world + me] = number of entries from rank s.  CELLS: CELL_F16 or CELL_U32.
+// The same fence for a rank that has no points this run (no route kernel to carry it).
+__global__ void route_signal_kernel(RouteDev rt) {
+    if ((int)threadIdx.x < rt.world) publish_frame(rt, (int)threadIdx.x);
+}
+
+// Counts the entries the ranks sent into this rank's band buffer: one warp per (source, region).
+// With `flags`, first waits until rank s has published this frame's epoch (bounded: on a timeout it
+// records the error and skips the source, so a dead peer cannot hang the GPU).  Count words are zeroed
+// as they are used: senders only ever write non-zero ones.  CELLS: CELL_F16 or CELL_U32.
 template <int CELLS>
 __global__ void __launch_bounds__(256)
-drain_inbox_kernel(const uint32_t* __restrict__ inbox, uint32_t capacity, const uint32_t* __restrict__ counts_all,
-                   int me, int world, uint32_t* __restrict__ band, uint32_t band_cells) {
+drain_inbox_kernel(const uint32_t* __restrict__ inbox, uint32_t* cnt, uint32_t nregion,
+                   const uint32_t* flags, uint32_t epoch, uint32_t* __restrict__ errors,
+                   uint32_t* __restrict__ band, uint32_t band_cells,
+                   uint4* __restrict__ other_band, uint32_t other_n16) {
     const int s = blockIdx.y;
-    const uint32_t n = min(counts_all[s * world + me], capacity);
-    const uint32_t* seg = inbox + (size_t)s * capacity;
+    // The band buffer is multi-buffered by splat frame: while this frame's entries go into `band`,
+    // the buffer an earlier frame composited from is zeroed for the next one (useful work to do
+    // before waiting for the peers).
+    for (uint32_t i = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < other_n16;
+         i += gridDim.x * gridDim.y * blockDim.x)
+        other_band[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (flags) {
+        __shared__ int arrived;
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            int ok = 1;
+            // epochs only grow; compare as signed distance so that wrap-around stays harmless.  The
+            // acquire load orders the reads of the entries (by the whole CTA, after the barrier) behind it.
+            while ((int32_t)(ld_acquire_sys(flags + s) - epoch) < 0) {
+                __nanosleep(100);
+                if (clock64() - t0 > 4000000000LL) { ok = 0; break; } // ~2 s
+            }
+            if (!ok) atomicAdd(errors, 1u);
+            arrived = ok;
+        }
+        __syncthreads();
+        if (!arrived) return;
+    }
+    // Regions of source s are dealt round-robin to the warps (neighbouring regions are busy together:
+    // the CTAs near a band edge).  A warp first loads the count words of up to 32 of its regions in one
+    // go (most are zero: far ranks send nothing), then works through the non-empty ones.
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarp = gridDim.x * (blockDim.x >> 5);
     const uint64_t keep = make_normal_policy();
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t e = __ldcs(seg + i);
-        if (e >= band_cells) continue;
-        if (CELLS == CELL_F16) cell_add_f16(band, (long long)e, keep);
-        else atomicAdd(band + e, 1u);
+    for (uint32_t k0 = 0; warp + k0 * nwarp < nregion; k0 += 32u) {
+        const uint32_t c = warp + (k0 + lane) * nwarp;
+        uint32_t* word = cnt + (size_t)s * nregion + c;
+        const uint32_t mine = (c < nregion) ? min(__ldcg(word), ROUTE_BLOCK) : 0u; // written by a peer: read at L2
+        if (mine) *word = 0u;
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, mine != 0u);
+        while (todo) {
+            const int r = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t n = __shfl_sync(0xFFFFFFFFu, mine, r);
+            const uint32_t* seg = inbox + ((size_t)s * nregion + warp + (k0 + (uint32_t)r) * nwarp) * ROUTE_BLOCK;
+            for (uint32_t i0 = 0; i0 < n; i0 += 256u) { // 8 loads in flight per lane: the loop is latency-bound
+                uint32_t e[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t i = i0 + (uint32_t)j * 32u + lane;
+                    e[j] = i < n ? __ldcg(seg + i) : 0xFFFFFFFFu;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (e[j] >= band_cells) continue;
+                    if (CELLS == CELL_F16) cell_add_f16(band, (long long)e[j], keep);
+                    else atomicAdd(band + e[j], 1u);
+                }
+            }
+        }
     }
 }
 
@@ -457,18 +565,31 @@ struct clumpy_advect {
     // ctx->stream.  advected[b]: counts of buffer b complete; cleared[b]: buffer b zeroed again.
     bool overlap = false, side_dirty = false;
     bool keep_cells = false;  // half-float counters are accessed with L2 evict-last hints
+    bool keep_pos = false;    // positions / phases are accessed with the normal L2 policy instead of
+                              // evict-first (when the whole working set of a rank fits in L2)
     bool count_open = false;  // advect_count was called, advect_finish_frame not yet
     // multi-GPU routing (clumpy_cuda_advect_route_*): this rank's inbox, band buffer and peers
     struct Route {
         bool on = false;
         int rank = 0, world = 1, chunk = 0;
-        uint32_t capacity = 0;
-        uint32_t* inbox = nullptr;   // [2 parities][world sources][capacity] cell indices
-        uint32_t* counts = nullptr;  // [2 parities][world destinations] entries sent this frame
-        uint32_t* band = nullptr;    // [halo | chunk | halo | slack] rows of counter cells
-        size_t band_bytes = 0;
+        uint32_t nregion = 0;        // regions of ROUTE_BLOCK entry slots per source segment
+        uint32_t* inbox = nullptr;   // [ROUTE_BANDS][world sources][nregion * ROUTE_BLOCK] cell indices, then
+                                     // [ROUTE_BANDS][world sources][nregion] count words, then [world] epoch flags
+        size_t entries_per_parity = 0, cnt_offset = 0, flags_offset = 0; // in uint32 units from `inbox`
+        uint32_t* counts = nullptr;  // [world] zeros: what clumpy_cuda_advect_route hands out for the caller's fence
+        uint32_t* band = nullptr;    // ROUTE_BANDS x [halo | chunk | halo | slack] rows of counter cells: frame s
+                                     // counts into one, its drain zeroes the next one, and the composites
+                                     // of earlier frames may still be reading theirs on the side stream
+        int band_cur = 0;            // which of them this splat frame counts into
+        cudaEvent_t routed = nullptr, drained[ROUTE_BANDS] = {};
+        bool drain_pending[ROUTE_BANDS] = {};
+        uint32_t* ticket = nullptr;  // CTAs of the route kernel done so far (fused fence)
+        size_t band_bytes = 0;       // bytes of ONE band buffer (a multiple of 256)
         uint32_t band_cells = 0;
         uint32_t* peer_inbox[ROUTE_MAX_WORLD] = {nullptr};
+        uint32_t* errors = nullptr;  // fence time-outs seen by this rank's drain kernels
+        uint32_t epoch_base = 0;
+        bool loopback = false;       // CLUMPY_ROUTE_LOOPBACK=1: see route_begin
     } route;
     bool clear_pending[2] = {false, false};
     cudaEvent_t advected[2] = {nullptr, nullptr}, cleared[2] = {nullptr, nullptr}, side_done = nullptr;
@@ -493,7 +614,10 @@ static void advect_release(clumpy_advect* a) {
     cudaFree(a->pos); cudaFree(a->orig); cudaFree(a->vel); cudaFree(a->offset); cudaFree(a->perm);
     cudaFree(a->pos_alt); cudaFree(a->orig_alt); cudaFree(a->offset_alt); cudaFree(a->perm_alt);
     cudaFree(a->sort_counts); cudaFree(a->sort_sums);
-    cudaFree(a->route.inbox); cudaFree(a->route.counts); cudaFree(a->route.band);
+    cudaFree(a->route.inbox); cudaFree(a->route.counts); cudaFree(a->route.band); cudaFree(a->route.errors);
+    cudaFree(a->route.ticket);
+    if (a->route.routed) cudaEventDestroy(a->route.routed);
+    for (int b = 0; b < ROUTE_BANDS; ++b) if (a->route.drained[b]) cudaEventDestroy(a->route.drained[b]);
     cudaFree(a->hist); cudaFree(a->img[0]); cudaFree(a->img[1]);
     free_dense_tables(&a->dense);
     for (int b = 0; b < 2; ++b) {
@@ -650,6 +774,7 @@ static int advect_begin_impl(clumpy_advect* a, const float* pts_host, const floa
         // 0.2173 ms per step), so off unless asked for.
         a->keep_cells = a->cell_mode == CELL_F16 && (kc ? kc[0] != '0' : false);
         ctx->keep_cells = a->keep_cells ? 1 : 0;
+        if (const char* kp = getenv("CLUMPY_CUDA_KEEP_POS")) a->keep_pos = kp[0] == '1';
         if (const char* cap = getenv("CLUMPY_CUDA_COMPOSITE_CTAS")) ctx->composite_ctas_per_sm = atoi(cap);
         else ctx->composite_ctas_per_sm = a->overlap ? 4 : 0;
     }
@@ -756,7 +881,7 @@ CLUMPY_API int clumpy_cuda_advect_begin(clumpy_cuda_ctx* ctx, const float* pts_h
 template <bool WRAP, int MODE, typename OffT>
 static void launch_advect_t(clumpy_advect* a, uint32_t phase) {
     const uint32_t grid = ceil_div(a->npts, ADVECT_THREADS * ADVECT_PTS);
-    const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch};
+    const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch, a->keep_pos ? 1 : 0};
     advect_kernel<WRAP, MODE, OffT><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
         a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase, g,
         a->hist_buf[a->cellbuf], a->dense.cell_cap, a->keep_cells ? 1 : 0);
@@ -999,21 +1124,38 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     clumpy_cuda_ctx* ctx = adv->ctx;
     CK(cudaSetDevice(ctx->device));
     auto& rt = adv->route;
-    rt.rank = rank; rt.world = world; rt.capacity = std::max<uint32_t>(capacity, 1u);
+    rt.rank = rank; rt.world = world;
+    rt.nregion = std::max<uint32_t>(ceil_div(capacity, ROUTE_BLOCK), 1u); // one region per CTA of the largest shard
     rt.chunk = adv->geom.rows / world;
     REQUIRE(world == 1 || rt.chunk >= 2 * adv->geom.halo, "bands thinner than the sprite are not supported");
     const size_t cell_bytes = adv->cell_mode == CELL_F16 ? 2 : 4;
     const size_t band_rows = (size_t)rt.chunk + 2 * adv->geom.halo + 32;
     rt.band_cells = (uint32_t)(band_rows * adv->geom.pitch);
     rt.band_bytes = round_up((size_t)rt.band_cells * cell_bytes, 256);
-    const size_t ibytes = 2ull * world * rt.capacity * sizeof(uint32_t);
+    rt.entries_per_parity = (size_t)world * rt.nregion * ROUTE_BLOCK;
+    rt.cnt_offset = ROUTE_BANDS * rt.entries_per_parity;
+    rt.flags_offset = round_up(rt.cnt_offset + (size_t)ROUTE_BANDS * world * rt.nregion, 64);
+    const size_t ibytes = round_up((rt.flags_offset + (size_t)world) * sizeof(uint32_t), 256);
     CK(cudaMalloc(&rt.inbox, ibytes));
-    CK(cudaMalloc(&rt.counts, 2ull * world * sizeof(uint32_t)));
-    CK(cudaMalloc(&rt.band, rt.band_bytes));
-    CK(cudaMemsetAsync(rt.counts, 0, 2ull * world * sizeof(uint32_t), ctx->stream));
-    CK(cudaMemsetAsync(rt.band, 0, rt.band_bytes, ctx->stream));
+    CK(cudaMalloc(&rt.counts, ROUTE_MAX_WORLD * sizeof(uint32_t)));
+    CK(cudaMalloc(&rt.band, ROUTE_BANDS * rt.band_bytes));
+    CK(cudaEventCreateWithFlags(&rt.routed, cudaEventDisableTiming));
+    for (int b = 0; b < ROUTE_BANDS; ++b) CK(cudaEventCreateWithFlags(&rt.drained[b], cudaEventDisableTiming));
+    CK(cudaMalloc(&rt.errors, sizeof(uint32_t)));
+    CK(cudaMalloc(&rt.ticket, sizeof(uint32_t)));
+    CK(cudaMemsetAsync(rt.ticket, 0, sizeof(uint32_t), ctx->stream));
+    // count words and flags start at zero (the entries need no initialisation)
+    CK(cudaMemsetAsync(rt.inbox + rt.cnt_offset, 0, ibytes - rt.cnt_offset * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(rt.errors, 0, sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(rt.counts, 0, ROUTE_MAX_WORLD * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(rt.band, 0, ROUTE_BANDS * rt.band_bytes, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     rt.peer_inbox[rank] = rt.inbox;
+    // Profiling aid (ncu must not run a multi-rank job): with CLUMPY_ROUTE_LOOPBACK=1 one process plays
+    // rank `rank` of `world` alone.  The caller maps its own inbox as every peer's; the fence then
+    // publishes all `world` epochs into its own flags.  Timing and memory traffic are about those of a
+    // real rank, the FRAMES ARE NOT (entries for other bands pile up in this rank's inbox).
+    if (const char* lb = getenv("CLUMPY_ROUTE_LOOPBACK")) rt.loopback = lb[0] == '1';
     rt.on = true;
     *inbox_dev = rt.inbox;
     *inbox_bytes = ibytes;
@@ -1030,70 +1172,200 @@ CLUMPY_API int clumpy_cuda_advect_route_peers(clumpy_advect* adv, void* const* p
 
 template <bool WRAP, bool SPLAT, typename OffT>
 static void launch_route_t(clumpy_advect* a, uint32_t phase, const RouteDev& rd) {
-    const uint32_t grid = ceil_div(a->npts, ADVECT_THREADS * ADVECT_PTS);
-    const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch};
+    const uint32_t grid = ceil_div(a->npts, ROUTE_BLOCK); // CTA c owns region c of its segments
+    const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch, a->keep_pos ? 1 : 0};
     advect_route_kernel<WRAP, SPLAT, OffT><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
         a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase, g, rd);
 }
 
-CLUMPY_API int clumpy_cuda_advect_route(clumpy_advect* adv, void** counts_dev) {
-    REQUIRE(adv && adv->route.on, "routing is not set up");
-    REQUIRE(!adv->count_open, "advect_route called twice without advect_drain");
+// One route launch.  fenced: the kernel itself publishes the frame's epoch to the peers (route_steps);
+// otherwise the caller fences with a collective of its own.
+static int route_launch(clumpy_advect* adv, bool fenced, uint32_t epoch, void** counts_dev) {
     clumpy_cuda_ctx* ctx = adv->ctx;
-    CK(cudaSetDevice(ctx->device));
     auto& rt = adv->route;
-    const int parity = (int)(adv->simframe & 1u);
-    RouteDev rd;
+    const int parity = rt.band_cur; // inbox parities and band buffers cycle together, one per splat frame
+    const bool splat = frame_splats(adv);
+    // This frame counts into band buffer `parity`, which the drain of two splat frames ago zeroed on
+    // the side stream; that drain also saw every peer's epoch of its frame, so every peer had by then
+    // finished the route kernel that FOLLOWED its own drain of four frames ago -- the one that last read
+    // the inbox parity this frame writes.  So this one wait covers both the band and the peers' inboxes.
+    const int back2 = (parity + 2) % ROUTE_BANDS;
+    if (splat && rt.drain_pending[back2]) {
+        CK(cudaStreamWaitEvent(ctx->stream, rt.drained[back2], 0));
+        rt.drain_pending[back2] = false;
+    }
+    RouteDev rd = {};
     rd.me = rt.rank; rd.world = rt.world; rd.chunk = rt.chunk; rd.halo = adv->geom.halo; rd.pitch = adv->geom.pitch;
-    rd.capacity = rt.capacity;
-    rd.counts = rt.counts + (size_t)parity * rt.world;
-    for (int r = 0; r < ROUTE_MAX_WORLD; ++r)
-        rd.inbox[r] = r < rt.world ? rt.peer_inbox[r] + (size_t)parity * rt.world * rt.capacity : nullptr;
-    CK(cudaMemsetAsync(rd.counts, 0, rt.world * sizeof(uint32_t), ctx->stream));
+    rd.nregion = rt.nregion;
+    rd.band = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(rt.band) + (size_t)rt.band_cur * rt.band_bytes);
+    rd.band_f16 = adv->cell_mode == CELL_F16 ? 1 : 0;
+    rd.signal = fenced ? 1 : 0;
+    rd.epoch = epoch;
+    rd.loopback = rt.loopback ? 1 : 0;
+    rd.ticket = rt.ticket;
+    for (int r = 0; r < rt.world; ++r) {
+        rd.inbox[r] = rt.peer_inbox[r] + (size_t)parity * rt.entries_per_parity;
+        rd.cnt[r] = rt.peer_inbox[r] + rt.cnt_offset + (size_t)parity * rt.world * rt.nregion;
+        rd.flags[r] = rt.peer_inbox[r] + rt.flags_offset;
+    }
     if (adv->npts) {
-        const bool splat = frame_splats(adv);
         const uint32_t phase = adv->simframe % adv->nframes;
 #define ROUTE_LAUNCH(W, S) (adv->off16 ? launch_route_t<W, S, uint16_t>(adv, phase, rd) : launch_route_t<W, S, uint32_t>(adv, phase, rd))
         if (adv->wrapx) { if (splat) ROUTE_LAUNCH(true, true); else ROUTE_LAUNCH(true, false); }
         else            { if (splat) ROUTE_LAUNCH(false, true); else ROUTE_LAUNCH(false, false); }
 #undef ROUTE_LAUNCH
         CK_LAUNCH(ctx);
+    } else if (fenced && splat) { // no route kernel to carry the fence
+        route_signal_kernel<<<1, 32, 0, ctx->stream>>>(rd);
+        CK_LAUNCH(ctx);
     }
     adv->count_open = true;
-    if (counts_dev) *counts_dev = rd.counts;
+    if (counts_dev) *counts_dev = rt.counts;
     return CLUMPY_OK;
 }
 
-CLUMPY_API int clumpy_cuda_advect_drain(clumpy_advect* adv, const uint32_t* counts_all_dev) {
-    REQUIRE(adv && adv->route.on && counts_all_dev, "routing is not set up");
-    REQUIRE(adv->count_open, "advect_drain without advect_route");
+CLUMPY_API int clumpy_cuda_advect_route(clumpy_advect* adv, void** counts_dev) {
+    REQUIRE(adv && adv->route.on, "routing is not set up");
+    REQUIRE(!adv->count_open, "advect_route called twice without advect_drain");
+    CK(cudaSetDevice(adv->ctx->device));
+    return route_launch(adv, false, 0u, counts_dev);
+}
+
+// fenced: wait for every source's epoch flag (device-side fence).  Also composites this rank's rows
+// and advances the frame.  Drain and composite run on the side stream (unless the kernels are being
+// timed one by one): the main stream carries only route kernels, back to back, and a rank may run up
+// to two frames ahead of its slowest peer before it has to wait.
+static int route_drain_impl(clumpy_advect* adv, bool fenced, uint32_t epoch, cudaEvent_t* ev = nullptr) {
     clumpy_cuda_ctx* ctx = adv->ctx;
-    CK(cudaSetDevice(ctx->device));
     auto& rt = adv->route;
     const int h = adv->geom.halo;
     if (frame_splats(adv)) {
-        const int parity = (int)(adv->simframe & 1u);
-        const uint32_t* inbox = rt.inbox + (size_t)parity * rt.world * rt.capacity;
-        const dim3 grid(std::min<uint32_t>(ceil_div(rt.capacity, 256), (uint32_t)ctx->sm_count * 2), rt.world);
+        const int cur = rt.band_cur, ahead = (cur + 2) % ROUTE_BANDS;
+        const uint32_t* inbox = rt.inbox + (size_t)cur * rt.entries_per_parity;
+        uint32_t* cnt = rt.inbox + rt.cnt_offset + (size_t)cur * rt.world * rt.nregion;
+        const uint32_t* flags = fenced ? rt.inbox + rt.flags_offset : nullptr;
+        // Band buffers: frame s counts into `cur`; its drain zeroes `ahead` for frame s+2 (last read by
+        // the composite of frame s-2, which precedes this drain on the side stream).
+        uint32_t* band = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(rt.band) + (size_t)cur * rt.band_bytes);
+        uint4* other = reinterpret_cast<uint4*>(reinterpret_cast<char*>(rt.band) + (size_t)ahead * rt.band_bytes);
+        const uint32_t other_n16 = (uint32_t)(rt.band_bytes / 16);
+        const bool overlap = adv->overlap && !ev;
+        const cudaStream_t main_stream = ctx->stream;
+        const cudaStream_t side = overlap ? ctx->aux_stream : main_stream;
+        if (overlap) {
+            CK(cudaEventRecord(rt.routed, main_stream));
+            CK(cudaStreamWaitEvent(side, rt.routed, 0));
+        }
+        // A small grid: these CTAs may sit waiting for a peer's epoch while the next route kernel runs
+        // on the main stream, and must leave it most of the SMs (256 CTAs of 1184 resident slots).
+        const dim3 grid(std::max<uint32_t>(1u, 256u / (uint32_t)rt.world), rt.world);
         if (adv->cell_mode == CELL_F16)
-            drain_inbox_kernel<CELL_F16><<<grid, 256, 0, ctx->stream>>>(inbox, rt.capacity, counts_all_dev, rt.rank, rt.world, rt.band, rt.band_cells);
+            drain_inbox_kernel<CELL_F16><<<grid, 256, 0, side>>>(inbox, cnt, rt.nregion, flags, epoch, rt.errors,
+                                                                  band, rt.band_cells, other, other_n16);
         else
-            drain_inbox_kernel<CELL_U32><<<grid, 256, 0, ctx->stream>>>(inbox, rt.capacity, counts_all_dev, rt.rank, rt.world, rt.band, rt.band_cells);
+            drain_inbox_kernel<CELL_U32><<<grid, 256, 0, side>>>(inbox, cnt, rt.nregion, flags, epoch, rt.errors,
+                                                                  band, rt.band_cells, other, other_n16);
         CK_LAUNCH(ctx);
+        if (overlap) {
+            CK(cudaEventRecord(rt.drained[cur], side));
+            rt.drain_pending[cur] = true;
+            adv->side_dirty = true;
+        }
+        if (ev) CK(cudaEventRecord(ev[2], main_stream));
         // image rows this rank owns: those whose window of padded rows lies in chunk + halos
         const int lo = rt.rank * rt.chunk;
         const int y0 = std::max(0, lo - h), y1 = std::min((int)adv->height, lo + rt.chunk - h);
         if (y1 > y0) {
             const size_t cell_bytes = adv->cell_mode == CELL_F16 ? 2 : 4;
-            const char* cells = reinterpret_cast<const char*>(rt.band) + (size_t)(y0 - (lo - h)) * adv->geom.pitch * cell_bytes;
+            const char* cells = reinterpret_cast<const char*>(band) + (size_t)(y0 - (lo - h)) * adv->geom.pitch * cell_bytes;
+            ctx->stream = side; // the launchers enqueue on ctx->stream
             int rc = clumpy_cuda_advect_composite_rows(adv, cells, (uint32_t)y0, (uint32_t)(y1 - y0));
+            ctx->stream = main_stream;
             if (rc) return rc;
         }
-        CK(cudaMemsetAsync(rt.band, 0, rt.band_bytes, ctx->stream));
+        rt.band_cur = (cur + 1) % ROUTE_BANDS;
+    } else if (ev) {
+        CK(cudaEventRecord(ev[2], ctx->stream));
     }
+    if (ev) CK(cudaEventRecord(ev[3], ctx->stream));
     adv->count_open = false;
     adv->simframe += 1;
     if (adv->regroup_every && ++adv->frames_since_regroup >= adv->regroup_every) return regroup_points(adv);
+    return CLUMPY_OK;
+}
+
+// The caller has fenced the frame itself (any collective on the context's stream that every rank
+// enters after its clumpy_cuda_advect_route); `counts_all_dev` is ignored and may be NULL.
+CLUMPY_API int clumpy_cuda_advect_drain(clumpy_advect* adv, const uint32_t* counts_all_dev) {
+    (void)counts_all_dev;
+    REQUIRE(adv && adv->route.on, "routing is not set up");
+    REQUIRE(adv->count_open, "advect_drain without advect_route");
+    CK(cudaSetDevice(adv->ctx->device));
+    int rc = route_drain_impl(adv, false, 0u);
+    return rc ? rc : advect_join(adv);
+}
+
+// `count` whole frames with the fence on the device: route on the main stream (its last CTA stores the
+// frame's epoch into every peer's flags); drain (zeroes the band buffer of the frame after next, waits
+// for every peer's epoch, counts the inbox) and composite on the side stream.  Three launches per
+// frame, no host-side collective, no synchronisation: the caller can enqueue thousands of frames in one call.
+static int route_steps_impl(clumpy_advect* adv, uint32_t count, cudaEvent_t* ev) {
+    REQUIRE(adv && adv->route.on, "routing is not set up");
+    REQUIRE(!adv->count_open, "advect_route_steps inside an open frame");
+    clumpy_cuda_ctx* ctx = adv->ctx;
+    CK(cudaSetDevice(ctx->device));
+    auto& rt = adv->route;
+    for (int r = 0; r < rt.world; ++r) REQUIRE(rt.peer_inbox[r], "peer inboxes are not mapped (route_peers)");
+    for (uint32_t i = 0; i < count; ++i) {
+        const uint32_t epoch = rt.epoch_base + adv->simframe + 1u;
+        cudaEvent_t* e = ev ? ev + 4 * (size_t)i : nullptr;
+        if (e) CK(cudaEventRecord(e[0], ctx->stream));
+        int rc = route_launch(adv, true, epoch, nullptr);
+        if (rc) return rc;
+        if (e) CK(cudaEventRecord(e[1], ctx->stream));
+        rc = route_drain_impl(adv, true, epoch, e);
+        if (rc) return rc;
+    }
+    return advect_join(adv); // whatever the caller enqueues next sees the finished framebuffer
+}
+
+CLUMPY_API int clumpy_cuda_advect_route_steps(clumpy_advect* adv, uint32_t count) {
+    return route_steps_impl(adv, count, nullptr);
+}
+
+// route_steps with CUDA events around every kernel: mean device time per frame (ms) of the route
+// kernel, the drain kernel (which includes the wait for the slowest peer) and the band composite.
+// Every rank must call it with the same count.  Synchronises.
+CLUMPY_API int clumpy_cuda_advect_route_profile(clumpy_advect* adv, uint32_t count, float* route_ms,
+                                                float* drain_ms, float* composite_ms) {
+    REQUIRE(adv && count > 0, "bad argument");
+    CK(cudaSetDevice(adv->ctx->device));
+    std::vector<cudaEvent_t> ev(4 * (size_t)count, nullptr);
+    int rc = CLUMPY_OK;
+    for (auto& e : ev)
+        if (cudaEventCreate(&e) != cudaSuccess) { set_error("event creation failed"); rc = CLUMPY_ERR_CUDA; break; }
+    if (rc == CLUMPY_OK) rc = route_steps_impl(adv, count, ev.data());
+    double t[3] = {0, 0, 0};
+    if (rc == CLUMPY_OK && cudaStreamSynchronize(adv->ctx->stream) != cudaSuccess) { set_error("profile run failed"); rc = CLUMPY_ERR_CUDA; }
+    for (uint32_t i = 0; rc == CLUMPY_OK && i < count; ++i)
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[4 * (size_t)i + k], ev[4 * (size_t)i + k + 1]);
+            t[k] += ms;
+        }
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (route_ms) *route_ms = (float)(t[0] / count);
+    if (drain_ms) *drain_ms = (float)(t[1] / count);
+    if (composite_ms) *composite_ms = (float)(t[2] / count);
+    return rc;
+}
+
+// Number of fence time-outs so far (a peer that never published its epoch).  Synchronises.
+CLUMPY_API int clumpy_cuda_advect_route_errors(clumpy_advect* adv, uint32_t* errors) {
+    REQUIRE(adv && errors && adv->route.on, "routing is not set up");
+    CK(cudaSetDevice(adv->ctx->device));
+    CK(cudaMemcpyAsync(errors, adv->route.errors, 4, cudaMemcpyDeviceToHost, adv->ctx->stream));
+    CK(cudaStreamSynchronize(adv->ctx->stream));
     return CLUMPY_OK;
 }
 

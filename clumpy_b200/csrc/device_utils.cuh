@@ -67,6 +67,7 @@ __device__ __forceinline__ void block_minmax_commit(float lo, bool has_lo, float
 // Geometry of the padded counter image (see splat.cu) as the kernels see it.
 struct GeomDev {
     int width, height, halo, pitch;
+    int keep_pos; // advect kernels: 1 = positions keep the normal L2 policy (default 0: evict-first stream)
 };
 
 // Index of the counter for a point whose truncated position is (cx, cy), or -1 when none of its

@@ -29,6 +29,30 @@ def shard_range(n, world, rank):
     return n * rank // world, n * (rank + 1) // world
 
 
+def shard_indices(pts, height, world, rank, how="home_rows"):
+    """Indices (ascending) of the points rank `rank` simulates.  The shards partition range(len(pts)).
+
+    "index":     contiguous index ranges -- no assumption about where points are.
+    "home_rows": rank r takes the points whose HOME row lies in the r-th of `world` horizontal strips,
+                 the strip edges being row quantiles of the cloud, so the shards are balanced (to within
+                 the points of one image row) whatever the density.  Points stay within a few hundred
+                 texels of home (they return there every nframes frames), so a rank's velocity gathers
+                 and counter updates stay inside about 1/world of the image -- small enough to live in
+                 L2 -- instead of paying a 32-byte sector of the whole field per point, and for a
+                 roughly uniform cloud most of a rank's entries are for its own band."""
+    n = len(pts)
+    if how == "index" or world == 1 or n == 0:
+        lo, hi = shard_range(n, world, rank)
+        return np.arange(lo, hi)
+    # same truncation as the splat (int32 cast); anything outside the image goes to the nearest row
+    y = np.nan_to_num(pts[:, 1].astype(np.float64), nan=0.0, posinf=float(height), neginf=0.0)
+    row = np.clip(y, 0, height - 1).astype(np.int64)
+    below = np.cumsum(np.bincount(row, minlength=height))  # points with home row <= y
+    # first row of strip r: the first row at which n*r/world points lie strictly above
+    edges = [int(np.searchsorted(below, n * r // world, side="right")) if r else 0 for r in range(world)] + [height]
+    return np.nonzero((row >= edges[rank]) & (row < edges[rank + 1]))[0]
+
+
 class BandPlan:
     """Row bands of the padded counter image (rows_alloc = world * chunk rows)."""
 
@@ -192,22 +216,35 @@ class RoutedAdvect:
         import clumpy_b200
         self.torch, self.dist = torch, dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        # profiling aid: one process plays rank r of w alone (CLUMPY_ROUTE_LOOPBACK=1 CLUMPY_ROUTE_LOOPBACK_AS=r/w);
+        # timing and traffic are a real rank's, the frames are not (see clumpy_cuda_advect_route_begin)
+        self.loopback = self.world == 1 and os.environ.get("CLUMPY_ROUTE_LOOPBACK") == "1"
+        if self.loopback:
+            self.rank, self.world = (int(v) for v in os.environ.get("CLUMPY_ROUTE_LOOPBACK_AS", "3/8").split("/"))
         self.ctx, self.device = ctx, device
         self.h_img, self.w_img = vel.shape[:2]
         n = self.n_total = len(pts)
-        lo, hi = shard_range(n, self.world, self.rank)
-        offsets = clumpy_b200.age_offsets(nframes, n)[lo:hi]
+        how = os.environ.get("CLUMPY_MULTIGPU_SHARD", "home_rows")
+        self.indices = shard_indices(pts, self.h_img, self.world, self.rank, how)
+        offsets = clumpy_b200.age_offsets(nframes, n)[self.indices]  # offsets follow the GLOBAL point index
         os.environ["CLUMPY_CUDA_CELLS"] = "f16" if kernel_size <= 3 else "u32"
-        os.environ["CLUMPY_CUDA_OVERLAP"] = "0"
         os.environ["CLUMPY_CUDA_CELL_ROWS_MULTIPLE"] = str(CELL_ROW_MULTIPLE * self.world)
-        self.adv = ctx.advect(np.ascontiguousarray(pts[lo:hi]), vel, step_size, kernel_size, decay, nframes,
-                              age_offset=offsets)
-        capacity = max(shard_range(n, self.world, r)[1] - shard_range(n, self.world, r)[0] for r in range(self.world))
+        self.adv = ctx.advect(np.ascontiguousarray(pts[self.indices]), vel, step_size, kernel_size, decay, nframes,
+                              age_offset=np.ascontiguousarray(offsets))
+        sizes = torch.zeros(self.world, dtype=torch.int64, device=device)
+        sizes[self.rank] = len(self.indices)
+        if self.world > 1 and not self.loopback:
+            dist.all_reduce(sizes)
+        self.shard_sizes = [int(v) for v in sizes.tolist()]
+        capacity = max(1, max(self.shard_sizes))
         inbox, _ = self.adv.route_begin(self.rank, self.world, capacity)
         # exchange CUDA IPC handles of the inboxes and map the peers'
-        handles = [None] * self.world
-        dist.all_gather_object(handles, ctx.ipc_export(inbox))
-        self.peer_ptrs = [inbox if r == self.rank else ctx.ipc_open(handles[r]) for r in range(self.world)]
+        if self.loopback:
+            self.peer_ptrs = [inbox] * self.world
+        else:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, ctx.ipc_export(inbox))
+            self.peer_ptrs = [inbox if r == self.rank else ctx.ipc_open(handles[r]) for r in range(self.world)]
         self.adv.route_peers(self.peer_ptrs)
         self.counts_all = torch.zeros((self.world, self.world), dtype=torch.int32, device=device)
         self.y0, self.y1 = self.adv.owned_rows()
@@ -216,7 +253,11 @@ class RoutedAdvect:
 
     def step(self, count=1):
         torch, dist = self.torch, self.dist
-        for _ in range(count):
+        if os.environ.get("CLUMPY_MULTIGPU_FENCE", "device") == "device":
+            # fence on the device (epoch flags in peer memory): one C call enqueues all the frames
+            self.adv.route_steps(count)
+            return
+        for _ in range(count):  # fence = NCCL all-gather of the entry counts, one round trip per frame
             ptr = self.adv.route()
             mine = self._counts_view.get(ptr)
             if mine is None:
@@ -232,21 +273,35 @@ class RoutedAdvect:
     gather_image = ShardedAdvect.gather_image
 
     def points(self):
+        """All positions in the caller's order (numpy), gathered from the shards."""
         torch, dist = self.torch, self.dist
-        mine = torch.from_numpy(self.adv.points()).to(self.device)
+        mine = self.adv.points()
         if self.world == 1:
-            return mine.cpu().numpy()
-        parts = [torch.empty((hi - lo, 2), dtype=torch.float32, device=self.device)
-                 for lo, hi in (shard_range(self.n_total, self.world, r) for r in range(self.world))]
-        dist.all_gather(parts, mine)
-        return torch.cat(parts).cpu().numpy()
+            return mine
+        cap = max(self.shard_sizes)
+        pos = torch.zeros((cap, 2), dtype=torch.float32, device=self.device)
+        idx = torch.zeros((cap,), dtype=torch.int64, device=self.device)
+        pos[:len(mine)] = torch.from_numpy(mine).to(self.device)
+        idx[:len(mine)] = torch.from_numpy(self.indices).to(self.device)
+        all_pos = torch.empty((self.world, cap, 2), dtype=torch.float32, device=self.device)
+        all_idx = torch.empty((self.world, cap), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(all_pos, pos)
+        dist.all_gather_into_tensor(all_idx, idx)
+        out = np.empty((self.n_total, 2), dtype=np.float32)
+        all_pos, all_idx = all_pos.cpu().numpy(), all_idx.cpu().numpy()
+        for r, m in enumerate(self.shard_sizes):
+            out[all_idx[r, :m]] = all_pos[r, :m]
+        return out
 
     def close(self):
         self.torch.cuda.synchronize()
-        if self.world > 1:
+        timeouts = self.adv.route_errors()
+        if self.world > 1 and not self.loopback:
             self.dist.barrier()  # nobody may still be writing into an inbox that is about to go away
+        if timeouts:
+            raise RuntimeError(f"rank {self.rank}: {timeouts} frame fences timed out (a peer stopped publishing)")
         for r, p in enumerate(self.peer_ptrs):
-            if r != self.rank and p:
+            if r != self.rank and p and not self.loopback:
                 self.ctx.ipc_close(p)
         self.adv.close()
 
@@ -272,6 +327,13 @@ def bench_multi(args, cfg, workload, metric, unit):
     torch.cuda.set_stream(stream)
     ctx = clumpy_b200.Context(local_rank, stream.cuda_stream)
     n, w, h = cfg["npts"], cfg["width"], cfg["height"]
+    # development aid (never set by the driver): CLUMPY_BENCH_ROWS_DIV=d runs 1/d of the workload --
+    # the top h/d rows of the field and n/d points -- so that `world` ranks see the per-rank working
+    # set of a (world * d)-rank run of the full workload.  The JSON line says so in config.workload.
+    rows_div = int(os.environ.get("CLUMPY_BENCH_ROWS_DIV", "1"))
+    if rows_div > 1:
+        n, h = n // rows_div, h // rows_div
+        workload = f"SCALED 1/{rows_div} (development run, not the benchmark): {n} points on {w}x{h}; " + workload
     K, W = args.steps, args.warmup
     hbm_peak, peak_src = measured_peaks()
 
@@ -279,7 +341,7 @@ def bench_multi(args, cfg, workload, metric, unit):
     # same seeded recipe on every rank and are sliced by the sharded run
     d_pot = torch.empty((h, w), dtype=torch.float32, device=device)
     d_vel = torch.empty((h, w, 2), dtype=torch.float32, device=device)
-    ctx.generate_simplex_dev(w, h, 0, h, cfg["amplitude"], cfg["frequency"], cfg["seed"], d_pot.data_ptr())
+    ctx.generate_simplex_dev(w, h, 0, h, cfg["amplitude"], cfg["frequency"] / rows_div, cfg["seed"], d_pot.data_ptr())
     ctx.curl_2d_dev(d_pot.data_ptr(), w, h, None, d_vel.data_ptr())
     vel = torch.empty((h, w, 2), dtype=torch.float32).pin_memory()
     vel.copy_(d_vel)
@@ -306,6 +368,15 @@ def bench_multi(args, cfg, workload, metric, unit):
     ms = float(ms.item())
     launches = ctx.launch_count() - launches0
     value = n * K / (ms * 1e-3)
+
+    # per-rank kernel times (CUDA events around every kernel; the drain includes the wait for the peers)
+    kernel_ms = None
+    if kind == "routed" and os.environ.get("CLUMPY_MULTIGPU_FENCE", "device") == "device":
+        t = torch.tensor(run.adv.route_profile(50), device=device)
+        allt = torch.empty((world, 3), device=device)
+        dist.all_gather_into_tensor(allt, t)
+        kernel_ms = {"route": allt[:, 0].tolist(), "drain_incl_wait": allt[:, 1].tolist(), "composite": allt[:, 2].tolist(),
+                     "points_per_rank": run.shard_sizes}
 
     # e2e: every rank also copies its band of each recorded frame to pinned host memory
     y0, y1 = run.y0, run.y1
@@ -352,7 +423,7 @@ def bench_multi(args, cfg, workload, metric, unit):
             "roofline": {"bound": "hbm", "kernel": "whole step (all ranks)", "peak": hbm_peak * world, "unit": "GB/s",
                          "achieved": (n * ALGO_BYTES_PER_POINT_STEP + w * h * ALGO_BYTES_PER_PIXEL_FRAME) / (ms / K * 1e-3) / 1e9,
                          "frac": (n * ALGO_BYTES_PER_POINT_STEP + w * h * ALGO_BYTES_PER_PIXEL_FRAME) / (ms / K * 1e-3) / 1e9 / (hbm_peak * world),
-                         "traffic": None, "peak_source": peak_src},
+                         "traffic": None, "peak_source": peak_src, "per_rank_kernel_ms": kernel_ms},
             "cpu_baseline": None,
         }
         print(json.dumps(line))

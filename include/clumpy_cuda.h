@@ -193,6 +193,20 @@ int clumpy_cuda_advect_route(clumpy_advect* adv, void** counts_dev);
 int clumpy_cuda_advect_drain(clumpy_advect* adv, const uint32_t* counts_all_dev);
 int clumpy_cuda_advect_owned_rows(clumpy_advect* adv, uint32_t* row0, uint32_t* nrows);
 
+/* The same frames with the fence on the DEVICE instead of a host-side collective: after its route
+ * kernel every rank stores its per-destination counts and the frame's epoch into the tail of each
+ * peer's inbox (a one-warp kernel, ordered after the route kernel by the stream), and the drain kernel
+ * waits for every source's epoch before reading its segment (bounded wait: ~2 s, then the segment is
+ * skipped and counted in route_errors, so a dead peer cannot hang the GPU).  `count` frames are
+ * enqueued by one call, with no host synchronisation and no NCCL on the data path. */
+int clumpy_cuda_advect_route_steps(clumpy_advect* adv, uint32_t count);
+/* route_steps with CUDA events around every kernel: mean device time per frame (ms) of the route
+ * kernel, the drain kernel (includes the wait for the slowest peer) and the band composite.  Every
+ * rank calls it with the same count.  Synchronises. */
+int clumpy_cuda_advect_route_profile(clumpy_advect* adv, uint32_t count, float* route_ms,
+                                     float* drain_ms, float* composite_ms);
+int clumpy_cuda_advect_route_errors(clumpy_advect* adv, uint32_t* errors);
+
 /* Device address of the current framebuffer (height * width u8), for callers that gather row
  * bands across GPUs themselves. */
 int clumpy_cuda_advect_image_dev(clumpy_advect* adv, void** img_dev);

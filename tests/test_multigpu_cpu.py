@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from clumpy_b200.multigpu import BandPlan, exchange_counts, shard_range
+from clumpy_b200.multigpu import BandPlan, exchange_counts, shard_indices, shard_range
 
 
 def test_shard_range_covers_everything():
@@ -21,6 +21,33 @@ def test_shard_range_covers_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("how", ["home_rows", "index"])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_shard_indices_partition_the_points(how, world):
+    rng = np.random.default_rng(5)
+    h = 200
+    clouds = {
+        "uniform": (rng.random((50000, 2)) * [300, h]).astype(np.float32),
+        "clustered": (rng.normal([150, 40], [30, 6], (50000, 2))).astype(np.float32),
+        "one_row": np.full((1000, 2), 17.5, np.float32),
+        "weird": np.array([[1, np.nan], [2, np.inf], [3, -np.inf], [4, -5], [5, 1e12], [6, 3.2]], np.float32),
+        "empty": np.zeros((0, 2), np.float32),
+    }
+    for name, pts in clouds.items():
+        parts = [shard_indices(pts, h, world, r, how) for r in range(world)]
+        merged = np.concatenate(parts) if parts else np.zeros(0, int)
+        assert sorted(merged.tolist()) == list(range(len(pts))), name
+        for part in parts:
+            assert (np.diff(part) > 0).all(), name  # ascending: a shard keeps the caller's relative order
+        if how == "home_rows" and name in ("uniform", "clustered"):
+            sizes = [len(p) for p in parts]
+            per_row = np.bincount(np.clip(pts[:, 1], 0, h - 1).astype(int), minlength=h).max()
+            assert max(sizes) - min(sizes) <= 2 * per_row + 1, (name, sizes)  # balanced to within a row of points
+            # a strip is a contiguous range of home rows
+            rows = [np.clip(pts[p, 1], 0, h - 1).astype(int) for p in parts if len(p)]
+            assert all(a.max() < b.min() for a, b in zip(rows, rows[1:])), name
 
 
 @pytest.mark.parametrize("height,halo,world", [(4096, 1, 8), (500, 0, 2), (500, 2, 3), (64, 3, 2), (2000, 3, 4), (37, 1, 2)])
