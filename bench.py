@@ -32,6 +32,10 @@ import time
 
 import numpy as np
 
+# The advect pipeline keeps kernels on three streams in flight (route / drain + composite / frame copy)
+# next to NCCL's and torch's own: give them hardware queues of their own (default 8 per process).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -301,7 +305,19 @@ def run_ours(args):
     return 0
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout, but libraries write there too (NCCL prints its version
+    line on stdout when NCCL_DEBUG=VERSION).  Point fd 1 at stderr for the duration of the run and keep
+    the real stdout for the final line: everything `print`ed from here on goes through `sys.stdout`,
+    which is re-opened on the saved descriptor."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)

@@ -1067,13 +1067,19 @@ CLUMPY_API int clumpy_cuda_advect_cells(clumpy_advect* adv, void** cells_dev, si
     return CLUMPY_OK;
 }
 
+static int composite_rows_impl(clumpy_advect* adv, const void* cells_dev, uint32_t row0, uint32_t nrows);
+
 CLUMPY_API int clumpy_cuda_advect_composite_rows(clumpy_advect* adv, const void* cells_dev,
                                                  uint32_t row0, uint32_t nrows) {
     REQUIRE(adv && cells_dev, "null argument");
     REQUIRE((uint64_t)row0 + nrows <= adv->height, "row band exceeds the image");
-    clumpy_cuda_ctx* ctx = adv->ctx;
-    CK(cudaSetDevice(ctx->device));
+    CK(cudaSetDevice(adv->ctx->device));
     if (!frame_splats(adv) || nrows == 0) return CLUMPY_OK;
+    return composite_rows_impl(adv, cells_dev, row0, nrows);
+}
+
+static int composite_rows_impl(clumpy_advect* adv, const void* cells_dev, uint32_t row0, uint32_t nrows) {
+    clumpy_cuda_ctx* ctx = adv->ctx;
     // the band as an image of its own: same width and pitch, `nrows` rows, cells given by the caller
     HistGeom g = adv->geom;
     g.height = (int)nrows;
@@ -1149,6 +1155,37 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     CK(cudaMemsetAsync(rt.errors, 0, sizeof(uint32_t), ctx->stream));
     CK(cudaMemsetAsync(rt.counts, 0, ROUTE_MAX_WORLD * sizeof(uint32_t), ctx->stream));
     CK(cudaMemsetAsync(rt.band, 0, ROUTE_BANDS * rt.band_bytes, ctx->stream));
+    // Load every kernel of the frame loop NOW.  With lazy module loading the first launch of a kernel
+    // can block the host until the device is idle -- and a drain kernel may be sitting on the device
+    // waiting for the epoch of a rank that this very host thread has yet to launch (one process
+    // driving several ranks).  The drain and the composite run once on the all-zero band, which leaves
+    // the (zero) framebuffer as it is; the route kernels are loaded without being run.
+    {
+        cudaFuncAttributes fa;
+#define ROUTE_LOAD(W, S) CK(adv->off16 ? cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, uint16_t>) \
+                                       : cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, uint32_t>))
+        if (adv->wrapx) { ROUTE_LOAD(true, true); ROUTE_LOAD(true, false); }
+        else            { ROUTE_LOAD(false, true); ROUTE_LOAD(false, false); }
+#undef ROUTE_LOAD
+        CK(cudaFuncGetAttributes(&fa, route_signal_kernel));
+        uint32_t* cnt0 = rt.inbox + rt.cnt_offset;
+        uint4* band1 = reinterpret_cast<uint4*>(reinterpret_cast<char*>(rt.band) + rt.band_bytes);
+        const dim3 grid(1, world);
+        if (adv->cell_mode == CELL_F16)
+            drain_inbox_kernel<CELL_F16><<<grid, 256, 0, ctx->stream>>>(rt.inbox, cnt0, rt.nregion, nullptr, 0u, rt.errors,
+                                                                         rt.band, rt.band_cells, band1, (uint32_t)(rt.band_bytes / 16));
+        else
+            drain_inbox_kernel<CELL_U32><<<grid, 256, 0, ctx->stream>>>(rt.inbox, cnt0, rt.nregion, nullptr, 0u, rt.errors,
+                                                                         rt.band, rt.band_cells, band1, (uint32_t)(rt.band_bytes / 16));
+        CK_LAUNCH(ctx);
+        const int h = adv->geom.halo, lo = rank * rt.chunk;
+        const int y0 = std::max(0, lo - h), y1 = std::min((int)adv->height, lo + rt.chunk - h);
+        if (y1 > y0) {
+            const char* cells = reinterpret_cast<const char*>(rt.band) + (size_t)(y0 - (lo - h)) * adv->geom.pitch * cell_bytes;
+            int rc = composite_rows_impl(adv, cells, (uint32_t)y0, (uint32_t)(y1 - y0));
+            if (rc) return rc;
+        }
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     rt.peer_inbox[rank] = rt.inbox;
     // Profiling aid (ncu must not run a multi-rank job): with CLUMPY_ROUTE_LOOPBACK=1 one process plays

@@ -5,6 +5,11 @@ import sys
 import numpy as np
 import pytest
 
+# tests/test_gpu_routed.py runs several ranks on one GPU, each with three streams of its own, and a
+# rank's drain kernel waits for the epoch another rank's route kernel publishes: the two streams must
+# not share a hardware work queue (the default is 8 queues per process).  Read at CUDA initialisation.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 if ROOT not in sys.path:

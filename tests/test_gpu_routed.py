@@ -1,0 +1,158 @@
+"""The multi-GPU advect path (exchange fused into the advect kernel, device-side frame fence) run as
+SEVERAL RANKS ON ONE GPU: every rank is a libclumpy_cuda context of its own (own streams) on cuda:0 and
+the "peer" inboxes are plain device pointers, so the whole protocol -- home-row sharding, own-band
+counting, per-CTA inbox regions, epoch flags, drain, band composite on the side stream, band buffers
+cycling -- runs for real and is compared with the CPU oracle frame by frame.  The same code over
+CUDA IPC / NVLink is checked by tools/check_multigpu.py under torchrun on a multi-GPU box.
+
+Reference semantics: commands/advect_points.cc:119-179 and splat_points.cc:118-161 (via oracle/)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import frame_agreement
+
+pytestmark = pytest.mark.gpu
+
+
+class RanksOnOneGpu:
+    def __init__(self, world, pts, vel, step, k, decay, nframes, monkeypatch, overlap, shard="home_rows"):
+        import clumpy_b200
+        from clumpy_b200.multigpu import CELL_ROW_MULTIPLE, shard_indices
+        monkeypatch.setenv("CLUMPY_CUDA_CELLS", "f16" if k <= 3 else "u32")
+        monkeypatch.setenv("CLUMPY_CUDA_OVERLAP", "1" if overlap else "0")
+        monkeypatch.setenv("CLUMPY_CUDA_CELL_ROWS_MULTIPLE", str(CELL_ROW_MULTIPLE * world))
+        self.world, self.n, self.h, self.w = world, len(pts), vel.shape[0], vel.shape[1]
+        offsets = clumpy_b200.age_offsets(nframes, len(pts))
+        self.ctxs = [clumpy_b200.Context(0) for _ in range(world)]
+        self.idx = [shard_indices(pts, self.h, world, r, shard) for r in range(world)]
+        self.advs = [c.advect(np.ascontiguousarray(pts[i]), vel, step, k, decay, nframes,
+                              age_offset=np.ascontiguousarray(offsets[i]))
+                     for c, i in zip(self.ctxs, self.idx)]
+        capacity = max(1, max(len(i) for i in self.idx))
+        inboxes = [a.route_begin(r, world, capacity)[0] for r, a in enumerate(self.advs)]
+        for a in self.advs:
+            a.route_peers(inboxes)
+        self.rows = [a.owned_rows() for a in self.advs]
+
+    def step(self, count=1):
+        # one frame at a time: a rank's drain waits (bounded) for the epochs of ranks enqueued after it
+        for _ in range(count):
+            for a in self.advs:
+                a.route_steps(1)
+
+    def image(self):
+        img = np.zeros((self.h, self.w), np.uint8)
+        for a, (y0, y1) in zip(self.advs, self.rows):
+            img[y0:y1] = a.image()[y0:y1]
+        return img
+
+    def points(self):
+        out = np.empty((self.n, 2), np.float32)
+        for a, i in zip(self.advs, self.idx):
+            out[i] = a.points()
+        return out
+
+    def close(self):
+        errors = [a.route_errors() for a in self.advs]
+        for a in self.advs:
+            a.close()
+        for c in self.ctxs:
+            c.close()
+        assert errors == [0] * self.world, f"frame fences timed out: {errors}"
+
+
+def _field(oracle_mod, w, h, seed=8):
+    pot, _, _ = oracle_mod.generate_simplex(w, h, 1.0, 5.0, seed)
+    vel, _, _ = oracle_mod.curl_2d(pot)
+    return vel
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+@pytest.mark.parametrize("world,w,h,n,k,decay,nframes,step", [
+    (2, 320, 200, 70001, 3, 0.98, 6, 35.0),
+    (3, 256, 160, 30000, 1, 0.9, 5, 40.0),
+    (4, 200, 136, 20000, 5, 0.95, 4, 30.0),
+    (2, 512, 64, 50000, 3, -0.97, 4, 60.0),     # negative decay: x-wrap mode
+    (8, 300, 520, 90000, 3, 0.97, 5, 90.0),     # eight bands, fast field: many points change band
+    (2, 128, 96, 5000, 3, 0.0, 3, 25.0),        # decay 0: warm-up frames do not splat at all
+])
+def test_ranks_on_one_gpu_match_oracle(oracle_mod, monkeypatch, overlap, world, w, h, n, k, decay, nframes, step):
+    vel = _field(oracle_mod, w, h)
+    # a cloud that also has points outside the image on every side
+    pts = ((np.random.default_rng(21).random((n, 2)) * 1.04 - 0.02) * [w, h]).astype(np.float32)
+    run = RanksOnOneGpu(world, pts, vel, step, k, decay, nframes, monkeypatch, overlap)
+    ref = oracle_mod.Advect(pts, vel, step, k, decay, nframes)
+    try:
+        for s in range(2 * nframes):
+            run.step()
+            ref.step()
+            assert np.array_equal(run.points().view(np.uint32), ref.points().view(np.uint32)), f"trajectories differ at frame {s}"
+            frac, worst = frame_agreement(run.image(), ref.image())
+            assert frac >= 0.999, f"frame {s}: only {frac:.5f} of the pixels within 1 LSB (max {worst})"
+            if k == 1:
+                assert worst == 0, f"frame {s}: k = 1 frames must be bit-identical"
+    finally:
+        ref.close()
+        run.close()
+
+
+def test_index_sharding_routes_everything_through_inboxes(oracle_mod, monkeypatch):
+    """Contiguous index ranges: a rank's points are all over the image, so (world-1)/world of them
+    travel through inboxes every frame."""
+    w, h, n, k, nframes = 256, 192, 60000, 3, 4
+    vel = _field(oracle_mod, w, h, seed=3)
+    pts = (np.random.default_rng(5).random((n, 2)) * [w, h]).astype(np.float32)
+    run = RanksOnOneGpu(4, pts, vel, 50.0, k, 0.96, nframes, monkeypatch, True, shard="index")
+    ref = oracle_mod.Advect(pts, vel, 50.0, k, 0.96, nframes)
+    try:
+        for s in range(2 * nframes):
+            run.step()
+            ref.step()
+        assert np.array_equal(run.points().view(np.uint32), ref.points().view(np.uint32))
+        frac, worst = frame_agreement(run.image(), ref.image())
+        assert frac >= 0.999, (frac, worst)
+    finally:
+        ref.close()
+        run.close()
+
+
+def test_all_points_in_one_band_and_an_empty_rank(oracle_mod, monkeypatch):
+    """Every point starts in the top rows: home-row sharding still balances the shards (strip edges are
+    row quantiles), bands 1.. receive nothing at first, and a rank whose shard is empty still takes
+    part in the fence."""
+    w, h, nframes = 200, 160, 4
+    vel = _field(oracle_mod, w, h, seed=11)
+    rng = np.random.default_rng(9)
+    pts = np.stack([rng.random(20000) * w, rng.random(20000) * 12.0], axis=1).astype(np.float32)
+    for world, cloud in ((4, pts), (4, pts[:2])):  # 2 points on 4 ranks: two shards are empty
+        run = RanksOnOneGpu(world, cloud, vel, 45.0, 3, 0.95, nframes, monkeypatch, False)
+        ref = oracle_mod.Advect(cloud, vel, 45.0, 3, 0.95, nframes)
+        try:
+            for s in range(2 * nframes):
+                run.step()
+                ref.step()
+                frac, worst = frame_agreement(run.image(), ref.image())
+                assert frac >= 0.999, (s, frac, worst)
+            assert np.array_equal(run.points().view(np.uint32), ref.points().view(np.uint32))
+        finally:
+            ref.close()
+            run.close()
+
+
+def test_dead_peer_times_out_instead_of_hanging(oracle_mod, monkeypatch):
+    """A rank whose peer never publishes its epoch must not hang the GPU: the drain gives up after its
+    bounded wait and the time-out is reported."""
+    w, h = 128, 96
+    vel = _field(oracle_mod, w, h)
+    pts = (np.random.default_rng(2).random((4000, 2)) * [w, h]).astype(np.float32)
+    run = RanksOnOneGpu(2, pts, vel, 20.0, 3, 0.9, 3, monkeypatch, False)
+    try:
+        run.advs[0].route_steps(1)      # rank 1 never runs this frame
+        assert run.advs[0].route_errors() >= 1
+    finally:
+        for a in run.advs:
+            a.close()
+        for c in run.ctxs:
+            c.close()

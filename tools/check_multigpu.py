@@ -10,6 +10,7 @@ trajectories: bit-identical).  Exits non-zero on any mismatch."""
 import os
 import sys
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import numpy as np
 import torch
 import torch.distributed as dist

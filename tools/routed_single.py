@@ -3,6 +3,7 @@
 the C4 points over the full image -- what each rank of an N-GPU run executes, minus the peers.  For
 profiling the per-rank kernels under ncu (a multi-rank run must not be profiled)."""
 import os, sys, socket, time
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import numpy as np, torch, torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
