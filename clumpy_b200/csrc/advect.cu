@@ -201,27 +201,39 @@ advect_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
 //
 // No global slot counters: CTA c of source rank s owns the fixed region [c * ROUTE_BLOCK,
 // (c + 1) * ROUTE_BLOCK) of segment s in every destination's inbox (a CTA advects ROUTE_BLOCK points and
-// a point sends at most one entry per destination), ranks its entries with a shared-memory atomic, and
-// leaves the number it wrote in the destination's count word [s][c].  The receiver reads the count
-// words, zeroes the ones it used, and counts the entries into its band.  The frame fence (an epoch
-// flag per source in the receiver's memory) is published by the last CTA of the kernel.
+// a point sends at most one entry per destination and frame), ranks its entries with a shared-memory
+// atomic, and leaves the number it wrote in the destination's count word [s][c].  The receiver reads
+// the count words, zeroes the ones it used, and counts the entries into its band.
+//
+// One launch advances the points by up to ROUTE_MAX_FUSE simulation frames: positions are loaded
+// once, stay in registers, and are stored once, and the launch overhead -- which at ~2 M points per
+// GPU (C4 on 8 GPUs) is as long as the work of a frame -- is paid once per group.  Every frame of the
+// group has its own band buffer, inbox parity, count words and ticket, and its own frame fence: an
+// epoch flag per source in the receiver's memory, published by the extra last CTA of the grid as
+// soon as all CTAs have finished that frame.
 constexpr int ROUTE_MAX_WORLD = 8;
 constexpr uint32_t ROUTE_BLOCK = ADVECT_THREADS * ADVECT_PTS; // points per CTA = entry slots per region
-constexpr int ROUTE_BANDS = 4;                                // band buffers in flight per rank
+constexpr int ROUTE_RING = 8;     // band buffers / inbox parities / tickets in flight per rank
+constexpr int ROUTE_AHEAD = 4;    // the drain of frame s zeroes the band buffer of frame s + ROUTE_AHEAD
+constexpr int ROUTE_MAX_FUSE = 4; // frames per launch (<= ROUTE_AHEAD)
 
 struct RouteDev {
     int me, world;
     int chunk, halo, pitch;             // band geometry in padded rows / cells
     uint32_t nregion;                   // regions (= CTAs of the largest shard) per source segment
-    uint32_t* inbox[ROUTE_MAX_WORLD];   // rank r's entries of this frame's parity (peer-mapped): [world][nregion * ROUTE_BLOCK]
-    uint32_t* cnt[ROUTE_MAX_WORLD];     // rank r's count words of this frame's parity (peer-mapped): [world][nregion]
+    uint32_t nframes, phase0;           // reset period; phase of the first frame of the group
+    int nf;                             // frames in this launch
+    int slot0;                          // ring slot of the first frame (frame f uses (slot0 + f) % ROUTE_RING)
+    size_t inbox_stride, cnt_stride, band_stride; // uint32 units between consecutive ring slots
+    uint32_t* inbox[ROUTE_MAX_WORLD];   // rank r's entries, ring slot 0 (peer-mapped): [ring][world][nregion * ROUTE_BLOCK]
+    uint32_t* cnt[ROUTE_MAX_WORLD];     // rank r's count words, ring slot 0 (peer-mapped): [ring][world][nregion]
     uint32_t* flags[ROUTE_MAX_WORLD];   // rank r's epoch flags (peer-mapped): [world]
-    uint32_t* band;                     // this rank's band buffer (points landing in my own band count directly)
+    uint32_t* band;                     // this rank's band buffers, ring slot 0
     int band_f16;                       // band cells are half floats (else uint32)
-    int signal;                         // 1: the last CTA publishes the epoch; 0: the caller fences
+    int signal;                         // 1: the grid has an extra CTA that publishes the epochs; 0: the caller fences
     int loopback;                       // profiling aid: every "peer" is this rank itself (see route_begin)
-    uint32_t epoch;
-    uint32_t* ticket;                   // CTAs done so far (reset by the last one)
+    uint32_t epoch0;                    // epoch of the first frame of the group
+    uint32_t* ticket;                   // [ring] CTAs that have finished the frame of that slot
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
@@ -231,105 +243,164 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 }
 
 // flags[me] = epoch in rank d's memory.  Called after every store of the frame has been fenced.
-__device__ __forceinline__ void publish_frame(const RouteDev& rt, int d) {
+__device__ __forceinline__ void publish_frame(const RouteDev& rt, int d, uint32_t epoch) {
     const int slot = rt.loopback ? d : rt.me; // loopback: play every source of my own inbox
-    *reinterpret_cast<volatile uint32_t*>(rt.flags[d] + slot) = rt.epoch;
+    *reinterpret_cast<volatile uint32_t*>(rt.flags[d] + slot) = epoch;
 }
+
+// What a frame of the group writes to.
+struct RouteFrame {
+    uint32_t* band;      // this rank's band buffer of the frame
+    size_t inbox_off;    // offset of the frame's parity inside every inbox / count-word array
+    size_t cnt_off;
+    uint32_t* cta_n;     // shared: entries this CTA has written per destination this frame
+};
 
 // One entry for rank `dst`: the CTA-wide rank comes from a shared-memory atomic, the slot is fixed by
 // the CTA's region, the store goes over NVLink.
-__device__ __forceinline__ void route_send(const RouteDev& rt, uint32_t* cta_n, int dst, uint32_t entry) {
-    const uint32_t r = atomicAdd(cta_n + dst, 1u);
-    rt.inbox[dst][((size_t)rt.me * rt.nregion + blockIdx.x) * ROUTE_BLOCK + r] = entry;
+__device__ __forceinline__ void route_send(const RouteDev& rt, const RouteFrame& fr, int dst, uint32_t entry) {
+    const uint32_t r = atomicAdd(fr.cta_n + dst, 1u);
+    rt.inbox[dst][fr.inbox_off + ((size_t)rt.me * rt.nregion + blockIdx.x) * ROUTE_BLOCK + r] = entry;
 }
 
 // A cell of padded row `r` (relative to band `owner`'s first row) and padded column `ux`: counted
 // straight into this rank's band buffer when it is ours, sent to the owner's inbox otherwise; rows
 // within the sprite's reach of a band edge also go to the neighbouring band, whose composite needs them.
-__device__ __forceinline__ void route_cell(const RouteDev& rt, uint32_t* cta_n, int owner, int r, uint32_t ux) {
+__device__ __forceinline__ void route_cell(const RouteDev& rt, const RouteFrame& fr, int owner, int r, uint32_t ux) {
     const uint32_t entry = (uint32_t)((r + rt.halo) * rt.pitch) + ux; // band rows: [halo above | chunk | halo below]
     if (owner == rt.me) {
-        if (rt.band_f16) cell_add_f16(rt.band, (long long)entry, make_normal_policy());
-        else atomicAdd(rt.band + entry, 1u);
+        if (rt.band_f16) cell_add_f16(fr.band, (long long)entry, make_normal_policy());
+        else atomicAdd(fr.band + entry, 1u);
     } else {
-        route_send(rt, cta_n, owner, entry);
+        route_send(rt, fr, owner, entry);
     }
-    if (r < rt.halo && owner > 0) route_send(rt, cta_n, owner - 1, (uint32_t)((r + rt.chunk + rt.halo) * rt.pitch) + ux);
-    if (r >= rt.chunk - rt.halo && owner < rt.world - 1) route_send(rt, cta_n, owner + 1, (uint32_t)((r - rt.chunk + rt.halo) * rt.pitch) + ux);
+    if (r < rt.halo && owner > 0) route_send(rt, fr, owner - 1, (uint32_t)((r + rt.chunk + rt.halo) * rt.pitch) + ux);
+    if (r >= rt.chunk - rt.halo && owner < rt.world - 1) route_send(rt, fr, owner + 1, (uint32_t)((r - rt.chunk + rt.halo) * rt.pitch) + ux);
 }
 
-template <bool WRAP, bool SPLAT, typename OffT>
-__global__ void __launch_bounds__(ADVECT_THREADS)
+// The extra last CTA of a fenced launch: for every frame of the group, wait until all the other CTAs
+// have finished it and publish its epoch to every peer (acquire = ticket read + fence here; release =
+// fence + ticket on the senders' side).
+__device__ __forceinline__ void route_publisher(const RouteDev& rt) {
+    if (threadIdx.x >= 32) return;
+    for (int f = 0; f < rt.nf; ++f) {
+        if (threadIdx.x == 0) {
+            uint32_t* t = rt.ticket + (rt.slot0 + f) % ROUTE_RING;
+            while (*reinterpret_cast<volatile uint32_t*>(t) != gridDim.x - 1u) __nanosleep(40);
+            *t = 0u;
+            __threadfence_system();
+        }
+        __syncwarp();
+        if ((int)threadIdx.x < rt.world) publish_frame(rt, (int)threadIdx.x, rt.epoch0 + (uint32_t)f);
+    }
+}
+
+template <bool WRAP, bool SPLAT, typename OffT, int MINB>
+__global__ void __launch_bounds__(ADVECT_THREADS, MINB)
 advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                     const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
-                    uint32_t width, uint32_t height, float step, uint32_t phase, GeomDev g, RouteDev rt) {
-    __shared__ uint32_t cta_n[ROUTE_MAX_WORLD]; // entries this CTA has written per destination
+                    uint32_t width, uint32_t height, float step, GeomDev g, RouteDev rt) {
+    __shared__ uint32_t cta_n[ROUTE_MAX_FUSE][ROUTE_MAX_WORLD];
+    if (SPLAT && rt.signal && blockIdx.x == gridDim.x - 1u) { route_publisher(rt); return; }
     if (SPLAT) {
-        if (threadIdx.x < ROUTE_MAX_WORLD) cta_n[threadIdx.x] = 0u;
+        if (threadIdx.x < ROUTE_MAX_FUSE * ROUTE_MAX_WORLD) (&cta_n[0][0])[threadIdx.x] = 0u;
         __syncthreads(); // here, where every warp arrives at once, not after the loads
     }
+    const uint64_t pol = g.keep_pos == 0 ? make_stream_policy() : make_normal_policy();
     const uint32_t base = blockIdx.x * ROUTE_BLOCK + threadIdx.x;
-    float2 p[ADVECT_PTS];
-    bool live[ADVECT_PTS];
-    advance_points<WRAP, OffT>(pos, orig, offset, npts, vel, width, height, step, phase, base, g.keep_pos == 0, p, live);
-    if (!SPLAT) return;
-
     const int my_lo = rt.me * rt.chunk; // first padded row of this rank's band
+    // positions and reset phases: loaded once for the whole group of frames
+    float2 p[ADVECT_PTS];
+    uint32_t off[ADVECT_PTS];
+    bool live[ADVECT_PTS];
 #pragma unroll
     for (int k = 0; k < ADVECT_PTS; ++k) {
-        // splat_points.cc:143-144: centre texel by (int32_t) truncation; same tests as hist_index
-        const int32_t cx = f2i32_x86(p[k].x), cy = f2i32_x86(p[k].y);
-        const uint32_t uy = (uint32_t)cy + (uint32_t)g.halo;
-        uint32_t ux;
-        bool inside = live[k] && uy < (uint32_t)(g.height + 2 * g.halo);
-        if (WRAP) {
-            int32_t m = cx % g.width;
-            if (m < 0) m += g.width;
-            ux = (uint32_t)(m + g.halo);
-        } else {
-            ux = (uint32_t)cx + (uint32_t)g.halo;
-            inside = inside && ux < (uint32_t)(g.width + 2 * g.halo);
-        }
-        if (!inside) continue;
-        const int r = (int)uy - my_lo;
-        if ((uint32_t)r < (uint32_t)rt.chunk) {
-            route_cell(rt, cta_n, rt.me, r, ux);
-        } else {
-            const int owner = min((int)(uy / (uint32_t)rt.chunk), rt.world - 1);
-            route_cell(rt, cta_n, owner, (int)uy - owner * rt.chunk, ux);
+        const uint32_t i = base + k * ADVECT_THREADS;
+        live[k] = i < npts;
+        p[k] = make_float2(0.f, 0.f);
+        off[k] = 0xFFFFFFFFu;
+        if (live[k]) {
+            p[k] = ld_stream_f2(pos + i, pol);
+            off[k] = ld_stream_off(offset + i, pol);
         }
     }
-    __syncthreads(); // all entries of this CTA are written, cta_n is final
-    if (threadIdx.x >= 32) return;
-    // Warp 0: leave the non-zero counts with their destinations (the receivers zero them again), then
-    // take part in the frame fence.  A CTA that stored into an inbox fences those stores at system scope
-    // (bar.sync / syncwarp order them before thread 0's cumulative fence.sys; CTAs whose points all
-    // landed in this rank's own band skip the fence, which costs microseconds) and then adds itself to
-    // the ticket with a fire-and-forget reduction.  The LAST CTA of the grid (dispatched last, so among
-    // the last to finish) waits until all the others have done so and publishes the frame's epoch to
-    // every peer: release = fence + ticket on the senders' side, acquire = ticket read + fence here.
-    const uint32_t n = (int)threadIdx.x < rt.world ? cta_n[threadIdx.x] : 0u;
-    if (n) *reinterpret_cast<volatile uint32_t*>(rt.cnt[threadIdx.x] + (size_t)rt.me * rt.nregion + blockIdx.x) = n;
-    const bool cta_sent = __any_sync(0xFFFFFFFFu, n != 0u);
-    if (!rt.signal) return;
-    if (threadIdx.x == 0 && cta_sent) __threadfence_system();
-    if (blockIdx.x != gridDim.x - 1u) {
-        if (threadIdx.x == 0) asm volatile("red.global.add.u32 [%0], 1;" :: "l"(rt.ticket) : "memory");
-        return;
+    uint32_t phase = rt.phase0;
+    for (int f = 0; f < rt.nf; ++f) {
+        // Euler step + reset, exactly as advance_points does it (advect_points.cc:144-153,163-171)
+        float2 v[ADVECT_PTS];
+#pragma unroll
+        for (int k = 0; k < ADVECT_PTS; ++k) { // nearest-texel fetch (advect_points.cc:23-37)
+            uint32_t x = f2u32_x86(p[k].x);
+            const uint32_t y = f2u32_x86(p[k].y);
+            if (WRAP) x = (width + (x % width)) % width;
+            v[k] = make_float2(0.f, 0.f);
+            if (live[k] && x < width && y < height) v[k] = __ldg(vel + ((size_t)y * width + x));
+        }
+#pragma unroll
+        for (int k = 0; k < ADVECT_PTS; ++k) {
+            // pt += step * v: rounded multiply, then rounded add (:146)
+            p[k] = make_float2(__fadd_rn(p[k].x, __fmul_rn(step, v[k].x)), __fadd_rn(p[k].y, __fmul_rn(step, v[k].y)));
+            if (off[k] == phase) p[k] = orig[base + k * ADVECT_THREADS]; // reset AFTER the move (:147-152,166-170)
+        }
+        phase = phase + 1u == rt.nframes ? 0u : phase + 1u;
+        if (!SPLAT) continue;
+
+        const int slot = (rt.slot0 + f) % ROUTE_RING;
+        RouteFrame fr;
+        fr.band = rt.band + (size_t)slot * rt.band_stride;
+        fr.inbox_off = (size_t)slot * rt.inbox_stride;
+        fr.cnt_off = (size_t)slot * rt.cnt_stride;
+        fr.cta_n = cta_n[f];
+#pragma unroll
+        for (int k = 0; k < ADVECT_PTS; ++k) {
+            // splat_points.cc:143-144: centre texel by (int32_t) truncation; same tests as hist_index
+            const int32_t cx = f2i32_x86(p[k].x), cy = f2i32_x86(p[k].y);
+            const uint32_t uy = (uint32_t)cy + (uint32_t)g.halo;
+            uint32_t ux;
+            bool inside = live[k] && uy < (uint32_t)(g.height + 2 * g.halo);
+            if (WRAP) {
+                int32_t m = cx % g.width;
+                if (m < 0) m += g.width;
+                ux = (uint32_t)(m + g.halo);
+            } else {
+                ux = (uint32_t)cx + (uint32_t)g.halo;
+                inside = inside && ux < (uint32_t)(g.width + 2 * g.halo);
+            }
+            if (!inside) continue;
+            const int r = (int)uy - my_lo;
+            if ((uint32_t)r < (uint32_t)rt.chunk) {
+                route_cell(rt, fr, rt.me, r, ux);
+            } else {
+                const int owner = min((int)(uy / (uint32_t)rt.chunk), rt.world - 1);
+                route_cell(rt, fr, owner, (int)uy - owner * rt.chunk, ux);
+            }
+        }
+        __syncthreads(); // all entries of this CTA for this frame are written, cta_n[f] is final
+        if (threadIdx.x < 32) {
+            // Warp 0 leaves the non-zero counts with their destinations (the receivers zero them again)
+            // and takes part in the frame fence while the other warps go on with the next frame.  A CTA
+            // that stored into an inbox fences those stores at system scope (bar.sync / syncwarp order
+            // them before thread 0's cumulative fence.sys; CTAs whose points all landed in this rank's own
+            // band skip the fence, which costs microseconds) and then adds itself to the frame's ticket
+            // with a fire-and-forget reduction.
+            const uint32_t n = (int)threadIdx.x < rt.world ? fr.cta_n[threadIdx.x] : 0u;
+            if (n) *reinterpret_cast<volatile uint32_t*>(rt.cnt[threadIdx.x] + fr.cnt_off + (size_t)rt.me * rt.nregion + blockIdx.x) = n;
+            const bool cta_sent = __any_sync(0xFFFFFFFFu, n != 0u);
+            if (rt.signal && threadIdx.x == 0) {
+                if (cta_sent) __threadfence_system();
+                asm volatile("red.global.add.u32 [%0], 1;" :: "l"(rt.ticket + slot) : "memory");
+            }
+        }
     }
-    if (threadIdx.x == 0) {
-        const volatile uint32_t* t = rt.ticket;
-        while (*t != gridDim.x - 1u) __nanosleep(40);
-        *rt.ticket = 0u;
-        __threadfence_system();
-    }
-    __syncwarp();
-    if ((int)threadIdx.x < rt.world) publish_frame(rt, (int)threadIdx.x);
+#pragma unroll
+    for (int k = 0; k < ADVECT_PTS; ++k)
+        if (live[k]) st_stream_f2(pos + base + k * ADVECT_THREADS, p[k], pol);
 }
 
 // The same fence for a rank that has no points this run (no route kernel to carry it).
 __global__ void route_signal_kernel(RouteDev rt) {
-    if ((int)threadIdx.x < rt.world) publish_frame(rt, (int)threadIdx.x);
+    for (int f = 0; f < rt.nf; ++f)
+        if ((int)threadIdx.x < rt.world) publish_frame(rt, (int)threadIdx.x, rt.epoch0 + (uint32_t)f);
 }
 
 // Counts the entries the ranks sent into this rank's band buffer: one warp per (source, region).
@@ -572,18 +643,19 @@ struct clumpy_advect {
     struct Route {
         bool on = false;
         int rank = 0, world = 1, chunk = 0;
+        int fuse = 1;                // frames per route launch (<= ROUTE_MAX_FUSE)
+        int minb = 6;                // route kernel variant: 6 CTAs per SM (40 registers; measured 2 % faster) or 8 (32)
         uint32_t nregion = 0;        // regions of ROUTE_BLOCK entry slots per source segment
-        uint32_t* inbox = nullptr;   // [ROUTE_BANDS][world sources][nregion * ROUTE_BLOCK] cell indices, then
-                                     // [ROUTE_BANDS][world sources][nregion] count words, then [world] epoch flags
-        size_t entries_per_parity = 0, cnt_offset = 0, flags_offset = 0; // in uint32 units from `inbox`
+        uint32_t* inbox = nullptr;   // [ROUTE_RING][world sources][nregion * ROUTE_BLOCK] cell indices, then
+                                     // [ROUTE_RING][world sources][nregion] count words, then [world] epoch flags
+        size_t entries_per_slot = 0, cnt_offset = 0, flags_offset = 0; // in uint32 units from `inbox`
         uint32_t* counts = nullptr;  // [world] zeros: what clumpy_cuda_advect_route hands out for the caller's fence
-        uint32_t* band = nullptr;    // ROUTE_BANDS x [halo | chunk | halo | slack] rows of counter cells: frame s
-                                     // counts into one, its drain zeroes the next one, and the composites
-                                     // of earlier frames may still be reading theirs on the side stream
-        int band_cur = 0;            // which of them this splat frame counts into
-        cudaEvent_t routed = nullptr, drained[ROUTE_BANDS] = {};
-        bool drain_pending[ROUTE_BANDS] = {};
-        uint32_t* ticket = nullptr;  // CTAs of the route kernel done so far (fused fence)
+        uint32_t* band = nullptr;    // ROUTE_RING x [halo | chunk | halo | slack] rows of counter cells: frame s
+                                     // counts into slot(s); its drain zeroes the buffer of frame s + ROUTE_AHEAD
+        int slot = 0;                // ring slot of the current splat frame
+        cudaEvent_t routed = nullptr, drained[ROUTE_RING] = {}, composited[ROUTE_RING] = {}, side2_done = nullptr;
+        bool drain_pending[ROUTE_RING] = {}, composite_pending[ROUTE_RING] = {}, side2_dirty = false;
+        uint32_t* ticket = nullptr;  // [ROUTE_RING] CTAs of the route kernel that have finished the slot's frame
         size_t band_bytes = 0;       // bytes of ONE band buffer (a multiple of 256)
         uint32_t band_cells = 0;
         uint32_t* peer_inbox[ROUTE_MAX_WORLD] = {nullptr};
@@ -616,8 +688,12 @@ static void advect_release(clumpy_advect* a) {
     cudaFree(a->sort_counts); cudaFree(a->sort_sums);
     cudaFree(a->route.inbox); cudaFree(a->route.counts); cudaFree(a->route.band); cudaFree(a->route.errors);
     cudaFree(a->route.ticket);
+    for (int b = 0; b < ROUTE_RING; ++b) {
+        if (a->route.drained[b]) cudaEventDestroy(a->route.drained[b]);
+        if (a->route.composited[b]) cudaEventDestroy(a->route.composited[b]);
+    }
+    if (a->route.side2_done) cudaEventDestroy(a->route.side2_done);
     if (a->route.routed) cudaEventDestroy(a->route.routed);
-    for (int b = 0; b < ROUTE_BANDS; ++b) if (a->route.drained[b]) cudaEventDestroy(a->route.drained[b]);
     cudaFree(a->hist); cudaFree(a->img[0]); cudaFree(a->img[1]);
     free_dense_tables(&a->dense);
     for (int b = 0; b < 2; ++b) {
@@ -984,6 +1060,11 @@ static int advect_one_frame(clumpy_advect* a, cudaEvent_t* ev = nullptr) {
 // Makes the main stream wait for everything issued on the side stream, so that whatever the caller
 // enqueues (or records) on the context's stream next is ordered after the whole frame.
 static int advect_join(clumpy_advect* a) {
+    if (a->route.side2_dirty) {
+        CK(cudaEventRecord(a->route.side2_done, a->ctx->aux2_stream));
+        CK(cudaStreamWaitEvent(a->ctx->stream, a->route.side2_done, 0));
+        a->route.side2_dirty = false;
+    }
     if (!a->side_dirty) return CLUMPY_OK;
     CK(cudaEventRecord(a->side_done, a->ctx->aux_stream));
     CK(cudaStreamWaitEvent(a->ctx->stream, a->side_done, 0));
@@ -1134,27 +1215,34 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     rt.nregion = std::max<uint32_t>(ceil_div(capacity, ROUTE_BLOCK), 1u); // one region per CTA of the largest shard
     rt.chunk = adv->geom.rows / world;
     REQUIRE(world == 1 || rt.chunk >= 2 * adv->geom.halo, "bands thinner than the sprite are not supported");
+    rt.fuse = ROUTE_MAX_FUSE;
+    if (const char* fz = getenv("CLUMPY_ROUTE_FUSE")) rt.fuse = std::min(std::max(atoi(fz), 1), ROUTE_MAX_FUSE);
+    if (const char* mb = getenv("CLUMPY_ROUTE_MINB")) rt.minb = atoi(mb) == 8 ? 8 : 6;
     const size_t cell_bytes = adv->cell_mode == CELL_F16 ? 2 : 4;
     const size_t band_rows = (size_t)rt.chunk + 2 * adv->geom.halo + 32;
     rt.band_cells = (uint32_t)(band_rows * adv->geom.pitch);
     rt.band_bytes = round_up((size_t)rt.band_cells * cell_bytes, 256);
-    rt.entries_per_parity = (size_t)world * rt.nregion * ROUTE_BLOCK;
-    rt.cnt_offset = ROUTE_BANDS * rt.entries_per_parity;
-    rt.flags_offset = round_up(rt.cnt_offset + (size_t)ROUTE_BANDS * world * rt.nregion, 64);
+    rt.entries_per_slot = (size_t)world * rt.nregion * ROUTE_BLOCK;
+    rt.cnt_offset = ROUTE_RING * rt.entries_per_slot;
+    rt.flags_offset = round_up(rt.cnt_offset + (size_t)ROUTE_RING * world * rt.nregion, 64);
     const size_t ibytes = round_up((rt.flags_offset + (size_t)world) * sizeof(uint32_t), 256);
     CK(cudaMalloc(&rt.inbox, ibytes));
     CK(cudaMalloc(&rt.counts, ROUTE_MAX_WORLD * sizeof(uint32_t)));
-    CK(cudaMalloc(&rt.band, ROUTE_BANDS * rt.band_bytes));
+    CK(cudaMalloc(&rt.band, ROUTE_RING * rt.band_bytes));
+    for (int b = 0; b < ROUTE_RING; ++b) {
+        CK(cudaEventCreateWithFlags(&rt.drained[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&rt.composited[b], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&rt.side2_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&rt.routed, cudaEventDisableTiming));
-    for (int b = 0; b < ROUTE_BANDS; ++b) CK(cudaEventCreateWithFlags(&rt.drained[b], cudaEventDisableTiming));
     CK(cudaMalloc(&rt.errors, sizeof(uint32_t)));
-    CK(cudaMalloc(&rt.ticket, sizeof(uint32_t)));
-    CK(cudaMemsetAsync(rt.ticket, 0, sizeof(uint32_t), ctx->stream));
+    CK(cudaMalloc(&rt.ticket, ROUTE_RING * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(rt.ticket, 0, ROUTE_RING * sizeof(uint32_t), ctx->stream));
     // count words and flags start at zero (the entries need no initialisation)
     CK(cudaMemsetAsync(rt.inbox + rt.cnt_offset, 0, ibytes - rt.cnt_offset * sizeof(uint32_t), ctx->stream));
     CK(cudaMemsetAsync(rt.errors, 0, sizeof(uint32_t), ctx->stream));
     CK(cudaMemsetAsync(rt.counts, 0, ROUTE_MAX_WORLD * sizeof(uint32_t), ctx->stream));
-    CK(cudaMemsetAsync(rt.band, 0, ROUTE_BANDS * rt.band_bytes, ctx->stream));
+    CK(cudaMemsetAsync(rt.band, 0, ROUTE_RING * rt.band_bytes, ctx->stream));
     // Load every kernel of the frame loop NOW.  With lazy module loading the first launch of a kernel
     // can block the host until the device is idle -- and a drain kernel may be sitting on the device
     // waiting for the epoch of a rank that this very host thread has yet to launch (one process
@@ -1162,8 +1250,10 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     // the (zero) framebuffer as it is; the route kernels are loaded without being run.
     {
         cudaFuncAttributes fa;
-#define ROUTE_LOAD(W, S) CK(adv->off16 ? cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, uint16_t>) \
-                                       : cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, uint32_t>))
+#define ROUTE_LOAD(W, S) CK(adv->off16 ? (rt.minb == 8 ? cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, uint16_t, 8>) \
+                                                        : cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, uint16_t, 6>)) \
+                                       : (rt.minb == 8 ? cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, uint32_t, 8>) \
+                                                        : cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, uint32_t, 6>)))
         if (adv->wrapx) { ROUTE_LOAD(true, true); ROUTE_LOAD(true, false); }
         else            { ROUTE_LOAD(false, true); ROUTE_LOAD(false, false); }
 #undef ROUTE_LOAD
@@ -1187,6 +1277,36 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
         }
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    // The texels a rank gathers lie in and around its own band of the field (home-row sharding): a
+    // few tens of MB that every frame reads again, while ~40 MB of positions stream past.  An L2
+    // persisting window over them (on the main stream, where only route kernels run) measured no
+    // difference on B200 (2 ranks, 1/4 of C4 each: 0.0411 vs 0.0408 ms per frame), so it is off unless
+    // CLUMPY_ROUTE_PERSIST_FIELD=1 (A/B runs).
+    {
+        const char* pf = getenv("CLUMPY_ROUTE_PERSIST_FIELD");
+        cudaDeviceProp prop;
+        if (world > 1 && (pf && pf[0] == '1') && cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess &&
+            prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+            const int h = adv->geom.halo, margin = std::max(16, rt.chunk / 4);
+            const long long r0 = std::max<long long>(0, (long long)rank * rt.chunk - h - margin);
+            const long long r1 = std::min<long long>(adv->height, (long long)(rank + 1) * rt.chunk - h + margin);
+            if (r1 > r0) {
+                const size_t row_bytes = (size_t)adv->width * sizeof(float2);
+                size_t window = std::min<size_t>((size_t)(r1 - r0) * row_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+                const size_t carve = std::min<size_t>(window, (size_t)prop.persistingL2CacheMaxSize);
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+                cudaStreamAttrValue attr = {};
+                attr.accessPolicyWindow.base_ptr = reinterpret_cast<char*>(adv->vel) + (size_t)r0 * row_bytes;
+                attr.accessPolicyWindow.num_bytes = window;
+                attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+                cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+                cudaGetLastError(); // best effort: a refusal only costs bandwidth
+                adv->l2_window = true;
+            }
+        }
+    }
     rt.peer_inbox[rank] = rt.inbox;
     // Profiling aid (ncu must not run a multi-rank job): with CLUMPY_ROUTE_LOOPBACK=1 one process plays
     // rank `rank` of `world` alone.  The caller maps its own inbox as every peer's; the fence then
@@ -1208,46 +1328,59 @@ CLUMPY_API int clumpy_cuda_advect_route_peers(clumpy_advect* adv, void* const* p
 }
 
 template <bool WRAP, bool SPLAT, typename OffT>
-static void launch_route_t(clumpy_advect* a, uint32_t phase, const RouteDev& rd) {
-    const uint32_t grid = ceil_div(a->npts, ROUTE_BLOCK); // CTA c owns region c of its segments
+static void launch_route_t(clumpy_advect* a, const RouteDev& rd) {
+    // CTA c owns region c of its segments; a fenced launch has one extra CTA, the publisher
+    const uint32_t grid = ceil_div(a->npts, ROUTE_BLOCK) + ((SPLAT && rd.signal) ? 1u : 0u);
     const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch, a->keep_pos ? 1 : 0};
-    advect_route_kernel<WRAP, SPLAT, OffT><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
-        a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase, g, rd);
+    if (a->route.minb == 8)
+        advect_route_kernel<WRAP, SPLAT, OffT, 8><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
+            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);
+    else
+        advect_route_kernel<WRAP, SPLAT, OffT, 6><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
+            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);
 }
 
-// One route launch.  fenced: the kernel itself publishes the frame's epoch to the peers (route_steps);
-// otherwise the caller fences with a collective of its own.
-static int route_launch(clumpy_advect* adv, bool fenced, uint32_t epoch, void** counts_dev) {
+// One route launch covering `nf` consecutive frames, starting at the current one.  fenced: the
+// kernel itself publishes every frame's epoch to the peers (route_steps); otherwise the caller fences
+// with a collective of its own (nf = 1).
+static int route_launch(clumpy_advect* adv, bool fenced, int nf, uint32_t epoch0) {
     clumpy_cuda_ctx* ctx = adv->ctx;
     auto& rt = adv->route;
-    const int parity = rt.band_cur; // inbox parities and band buffers cycle together, one per splat frame
     const bool splat = frame_splats(adv);
-    // This frame counts into band buffer `parity`, which the drain of two splat frames ago zeroed on
-    // the side stream; that drain also saw every peer's epoch of its frame, so every peer had by then
-    // finished the route kernel that FOLLOWED its own drain of four frames ago -- the one that last read
-    // the inbox parity this frame writes.  So this one wait covers both the band and the peers' inboxes.
-    const int back2 = (parity + 2) % ROUTE_BANDS;
-    if (splat && rt.drain_pending[back2]) {
-        CK(cudaStreamWaitEvent(ctx->stream, rt.drained[back2], 0));
-        rt.drain_pending[back2] = false;
+    const int slot0 = rt.slot; // ring slots (band buffer, inbox parity, count words, ticket) cycle per splat frame
+    // Frame s counts into band buffer slot(s), which the drain of frame s - ROUTE_AHEAD zeroed on its
+    // side stream; that drain also saw every peer's epoch of its frame, so every peer had by then
+    // launched -- after ITS drain of ROUTE_AHEAD frames earlier -- the kernel covering that frame, and
+    // so is done reading the inbox slot this frame writes (ROUTE_RING = 2 * ROUTE_AHEAD frames back).
+    // Drains complete in order, so waiting for the one the LAST frame of the group needs covers them all.
+    if (splat) {
+        const int need = (slot0 + nf - 1 + ROUTE_RING - ROUTE_AHEAD) % ROUTE_RING;
+        if (rt.drain_pending[need]) {
+            CK(cudaStreamWaitEvent(ctx->stream, rt.drained[need], 0));
+            rt.drain_pending[need] = false;
+        }
     }
     RouteDev rd = {};
     rd.me = rt.rank; rd.world = rt.world; rd.chunk = rt.chunk; rd.halo = adv->geom.halo; rd.pitch = adv->geom.pitch;
     rd.nregion = rt.nregion;
-    rd.band = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(rt.band) + (size_t)rt.band_cur * rt.band_bytes);
+    rd.nframes = adv->nframes; rd.phase0 = adv->simframe % adv->nframes;
+    rd.nf = nf; rd.slot0 = slot0;
+    rd.inbox_stride = rt.entries_per_slot;
+    rd.cnt_stride = (size_t)rt.world * rt.nregion;
+    rd.band_stride = rt.band_bytes / sizeof(uint32_t);
+    rd.band = rt.band;
     rd.band_f16 = adv->cell_mode == CELL_F16 ? 1 : 0;
     rd.signal = fenced ? 1 : 0;
-    rd.epoch = epoch;
+    rd.epoch0 = epoch0;
     rd.loopback = rt.loopback ? 1 : 0;
     rd.ticket = rt.ticket;
     for (int r = 0; r < rt.world; ++r) {
-        rd.inbox[r] = rt.peer_inbox[r] + (size_t)parity * rt.entries_per_parity;
-        rd.cnt[r] = rt.peer_inbox[r] + rt.cnt_offset + (size_t)parity * rt.world * rt.nregion;
+        rd.inbox[r] = rt.peer_inbox[r];
+        rd.cnt[r] = rt.peer_inbox[r] + rt.cnt_offset;
         rd.flags[r] = rt.peer_inbox[r] + rt.flags_offset;
     }
     if (adv->npts) {
-        const uint32_t phase = adv->simframe % adv->nframes;
-#define ROUTE_LAUNCH(W, S) (adv->off16 ? launch_route_t<W, S, uint16_t>(adv, phase, rd) : launch_route_t<W, S, uint32_t>(adv, phase, rd))
+#define ROUTE_LAUNCH(W, S) (adv->off16 ? launch_route_t<W, S, uint16_t>(adv, rd) : launch_route_t<W, S, uint32_t>(adv, rd))
         if (adv->wrapx) { if (splat) ROUTE_LAUNCH(true, true); else ROUTE_LAUNCH(true, false); }
         else            { if (splat) ROUTE_LAUNCH(false, true); else ROUTE_LAUNCH(false, false); }
 #undef ROUTE_LAUNCH
@@ -1256,8 +1389,6 @@ static int route_launch(clumpy_advect* adv, bool fenced, uint32_t epoch, void** 
         route_signal_kernel<<<1, 32, 0, ctx->stream>>>(rd);
         CK_LAUNCH(ctx);
     }
-    adv->count_open = true;
-    if (counts_dev) *counts_dev = rt.counts;
     return CLUMPY_OK;
 }
 
@@ -1265,36 +1396,42 @@ CLUMPY_API int clumpy_cuda_advect_route(clumpy_advect* adv, void** counts_dev) {
     REQUIRE(adv && adv->route.on, "routing is not set up");
     REQUIRE(!adv->count_open, "advect_route called twice without advect_drain");
     CK(cudaSetDevice(adv->ctx->device));
-    return route_launch(adv, false, 0u, counts_dev);
+    int rc = route_launch(adv, false, 1, 0u);
+    if (rc) return rc;
+    adv->count_open = true;
+    if (counts_dev) *counts_dev = adv->route.counts;
+    return CLUMPY_OK;
 }
 
-// fenced: wait for every source's epoch flag (device-side fence).  Also composites this rank's rows
-// and advances the frame.  Drain and composite run on the side stream (unless the kernels are being
-// timed one by one): the main stream carries only route kernels, back to back, and a rank may run up
-// to two frames ahead of its slowest peer before it has to wait.
-static int route_drain_impl(clumpy_advect* adv, bool fenced, uint32_t epoch, cudaEvent_t* ev = nullptr) {
+// The receiving half of the current frame: drain this rank's inbox into the frame's band buffer and
+// composite the rows this rank owns.  fenced: the drain waits for every source's epoch flag on the
+// device, and (for big clouds) drains run on one side stream and composites on another, ordered by
+// the flags and by events only: the main stream carries nothing but route kernels, the three stages of
+// consecutive frames overlap, and a rank may run several frames ahead of its slowest peer.
+static int route_receive(clumpy_advect* adv, bool fenced, uint32_t epoch, cudaEvent_t* ev = nullptr) {
     clumpy_cuda_ctx* ctx = adv->ctx;
     auto& rt = adv->route;
     const int h = adv->geom.halo;
     if (frame_splats(adv)) {
-        const int cur = rt.band_cur, ahead = (cur + 2) % ROUTE_BANDS;
-        const uint32_t* inbox = rt.inbox + (size_t)cur * rt.entries_per_parity;
+        const int cur = rt.slot, ahead = (cur + ROUTE_AHEAD) % ROUTE_RING;
+        const uint32_t* inbox = rt.inbox + (size_t)cur * rt.entries_per_slot;
         uint32_t* cnt = rt.inbox + rt.cnt_offset + (size_t)cur * rt.world * rt.nregion;
         const uint32_t* flags = fenced ? rt.inbox + rt.flags_offset : nullptr;
-        // Band buffers: frame s counts into `cur`; its drain zeroes `ahead` for frame s+2 (last read by
-        // the composite of frame s-2, which precedes this drain on the side stream).
+        // Band buffers: frame s counts into `cur`; its drain zeroes `ahead` for frame s + ROUTE_AHEAD
+        // (last read by the composite of frame s - ROUTE_AHEAD).
         uint32_t* band = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(rt.band) + (size_t)cur * rt.band_bytes);
         uint4* other = reinterpret_cast<uint4*>(reinterpret_cast<char*>(rt.band) + (size_t)ahead * rt.band_bytes);
         const uint32_t other_n16 = (uint32_t)(rt.band_bytes / 16);
-        const bool overlap = adv->overlap && !ev;
+        const bool overlap = adv->overlap && fenced && !ev;
         const cudaStream_t main_stream = ctx->stream;
-        const cudaStream_t side = overlap ? ctx->aux_stream : main_stream;
-        if (overlap) {
-            CK(cudaEventRecord(rt.routed, main_stream));
-            CK(cudaStreamWaitEvent(side, rt.routed, 0));
+        const cudaStream_t side = overlap ? ctx->aux_stream : main_stream;   // drains
+        const cudaStream_t side2 = overlap ? ctx->aux2_stream : main_stream; // composites
+        if (overlap && rt.composite_pending[ahead]) {
+            CK(cudaStreamWaitEvent(side, rt.composited[ahead], 0));
+            rt.composite_pending[ahead] = false;
         }
-        // A small grid: these CTAs may sit waiting for a peer's epoch while the next route kernel runs
-        // on the main stream, and must leave it most of the SMs (256 CTAs of 1184 resident slots).
+        // A small grid: these CTAs may sit waiting for a peer's epoch while route kernels run on the
+        // main stream, and must leave them most of the SMs (256 CTAs of 1184 resident slots).
         const dim3 grid(std::max<uint32_t>(1u, 256u / (uint32_t)rt.world), rt.world);
         if (adv->cell_mode == CELL_F16)
             drain_inbox_kernel<CELL_F16><<<grid, 256, 0, side>>>(inbox, cnt, rt.nregion, flags, epoch, rt.errors,
@@ -1313,21 +1450,26 @@ static int route_drain_impl(clumpy_advect* adv, bool fenced, uint32_t epoch, cud
         const int lo = rt.rank * rt.chunk;
         const int y0 = std::max(0, lo - h), y1 = std::min((int)adv->height, lo + rt.chunk - h);
         if (y1 > y0) {
+            if (overlap) CK(cudaStreamWaitEvent(side2, rt.drained[cur], 0));
             const size_t cell_bytes = adv->cell_mode == CELL_F16 ? 2 : 4;
             const char* cells = reinterpret_cast<const char*>(band) + (size_t)(y0 - (lo - h)) * adv->geom.pitch * cell_bytes;
-            ctx->stream = side; // the launchers enqueue on ctx->stream
+            ctx->stream = side2; // the launchers enqueue on ctx->stream
             int rc = clumpy_cuda_advect_composite_rows(adv, cells, (uint32_t)y0, (uint32_t)(y1 - y0));
             ctx->stream = main_stream;
             if (rc) return rc;
+            if (overlap) {
+                CK(cudaEventRecord(rt.composited[cur], side2));
+                rt.composite_pending[cur] = true;
+                rt.side2_dirty = true;
+            }
         }
-        rt.band_cur = (cur + 1) % ROUTE_BANDS;
+        rt.slot = (cur + 1) % ROUTE_RING;
     } else if (ev) {
         CK(cudaEventRecord(ev[2], ctx->stream));
     }
     if (ev) CK(cudaEventRecord(ev[3], ctx->stream));
-    adv->count_open = false;
     adv->simframe += 1;
-    if (adv->regroup_every && ++adv->frames_since_regroup >= adv->regroup_every) return regroup_points(adv);
+    ++adv->frames_since_regroup;
     return CLUMPY_OK;
 }
 
@@ -1338,14 +1480,22 @@ CLUMPY_API int clumpy_cuda_advect_drain(clumpy_advect* adv, const uint32_t* coun
     REQUIRE(adv && adv->route.on, "routing is not set up");
     REQUIRE(adv->count_open, "advect_drain without advect_route");
     CK(cudaSetDevice(adv->ctx->device));
-    int rc = route_drain_impl(adv, false, 0u);
-    return rc ? rc : advect_join(adv);
+    int rc = route_receive(adv, false, 0u);
+    adv->count_open = false;
+    if (rc) return rc;
+    if (adv->regroup_every && adv->frames_since_regroup >= adv->regroup_every) {
+        rc = regroup_points(adv);
+        if (rc) return rc;
+    }
+    return advect_join(adv);
 }
 
-// `count` whole frames with the fence on the device: route on the main stream (its last CTA stores the
-// frame's epoch into every peer's flags); drain (zeroes the band buffer of the frame after next, waits
-// for every peer's epoch, counts the inbox) and composite on the side stream.  Three launches per
-// frame, no host-side collective, no synchronisation: the caller can enqueue thousands of frames in one call.
+// `count` whole frames with the fence on the device.  Frames are launched in groups of up to
+// route.fuse: ONE route kernel advances the points through the group on the main stream (its extra
+// last CTA stores each frame's epoch into every peer's flags as soon as all CTAs have finished that
+// frame); per frame, a drain (zeroes the band buffer of the frame ROUTE_AHEAD frames on, waits for
+// every peer's epoch, counts the inbox) and a composite run on the two side streams.  No host-side
+// collective, no synchronisation: the caller can enqueue thousands of frames in one call.
 static int route_steps_impl(clumpy_advect* adv, uint32_t count, cudaEvent_t* ev) {
     REQUIRE(adv && adv->route.on, "routing is not set up");
     REQUIRE(!adv->count_open, "advect_route_steps inside an open frame");
@@ -1353,15 +1503,33 @@ static int route_steps_impl(clumpy_advect* adv, uint32_t count, cudaEvent_t* ev)
     CK(cudaSetDevice(ctx->device));
     auto& rt = adv->route;
     for (int r = 0; r < rt.world; ++r) REQUIRE(rt.peer_inbox[r], "peer inboxes are not mapped (route_peers)");
-    for (uint32_t i = 0; i < count; ++i) {
-        const uint32_t epoch = rt.epoch_base + adv->simframe + 1u;
+    for (uint32_t i = 0; i < count;) {
+        // a group never crosses a regroup or the warm-up / recording boundary (where, with decay 0,
+        // frames start to splat) and is timed frame by frame when profiling
+        uint32_t nf = ev ? 1u : std::min<uint32_t>((uint32_t)rt.fuse, count - i);
+        nf = std::min<uint32_t>(nf, adv->nframes - adv->simframe % adv->nframes);
+        if (adv->regroup_every) nf = std::min<uint32_t>(nf, std::max<uint32_t>(1u, adv->regroup_every - std::min(adv->frames_since_regroup, adv->regroup_every - 1u)));
+        const uint32_t epoch0 = rt.epoch_base + adv->simframe + 1u;
         cudaEvent_t* e = ev ? ev + 4 * (size_t)i : nullptr;
         if (e) CK(cudaEventRecord(e[0], ctx->stream));
-        int rc = route_launch(adv, true, epoch, nullptr);
+        int rc = route_launch(adv, true, (int)nf, epoch0);
         if (rc) return rc;
         if (e) CK(cudaEventRecord(e[1], ctx->stream));
-        rc = route_drain_impl(adv, true, epoch, e);
-        if (rc) return rc;
+        // The drains of the group start once its route kernel is done (by then this rank's own epochs
+        // are out; a drain that started earlier would only sit on SM slots waiting for them).
+        if (adv->overlap && !ev && frame_splats(adv)) {
+            CK(cudaEventRecord(rt.routed, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->aux_stream, rt.routed, 0));
+        }
+        for (uint32_t f = 0; f < nf; ++f) {
+            rc = route_receive(adv, true, epoch0 + f, e);
+            if (rc) return rc;
+        }
+        if (adv->regroup_every && adv->frames_since_regroup >= adv->regroup_every) {
+            rc = regroup_points(adv);
+            if (rc) return rc;
+        }
+        i += nf;
     }
     return advect_join(adv); // whatever the caller enqueues next sees the finished framebuffer
 }
@@ -1372,7 +1540,7 @@ CLUMPY_API int clumpy_cuda_advect_route_steps(clumpy_advect* adv, uint32_t count
 
 // route_steps with CUDA events around every kernel: mean device time per frame (ms) of the route
 // kernel, the drain kernel (which includes the wait for the slowest peer) and the band composite.
-// Every rank must call it with the same count.  Synchronises.
+// Frames are launched one by one here.  Every rank must call it with the same count.  Synchronises.
 CLUMPY_API int clumpy_cuda_advect_route_profile(clumpy_advect* adv, uint32_t count, float* route_ms,
                                                 float* drain_ms, float* composite_ms) {
     REQUIRE(adv && count > 0, "bad argument");

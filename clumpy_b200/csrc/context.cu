@@ -94,6 +94,7 @@ CLUMPY_API int clumpy_cuda_create(int device, void* stream, clumpy_cuda_ctx** ou
         int least = 0, greatest = 0;
         CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
         CK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, greatest));
+        CK(cudaStreamCreateWithPriority(&ctx->aux2_stream, cudaStreamNonBlocking, greatest));
     }
     CK(cudaEventCreate(&ctx->t0));
     CK(cudaEventCreate(&ctx->t1));
@@ -109,9 +110,11 @@ CLUMPY_API void clumpy_cuda_destroy(clumpy_cuda_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->aux_stream);
+    cudaStreamSynchronize(ctx->aux2_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->aux_stream);
+    cudaStreamDestroy(ctx->aux2_stream);
     cudaEventDestroy(ctx->t0);
     cudaEventDestroy(ctx->t1);
     cudaFree(ctx->d_minmax);

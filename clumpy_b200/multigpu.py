@@ -17,6 +17,7 @@ gloo backend in tests/test_multigpu_cpu.py; the device work goes through the C A
 """
 import json
 import os
+import sys
 import time
 
 import numpy as np
@@ -319,6 +320,7 @@ def bench_multi(args, cfg, workload, metric, unit):
     import clumpy_b200
     from bench import ALGO_BYTES_PER_PIXEL_FRAME, ALGO_BYTES_PER_POINT_STEP, ClockSampler, measured_peaks, synth_points
 
+    t_start = time.perf_counter()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     device = torch.device("cuda", local_rank)
@@ -349,13 +351,21 @@ def bench_multi(args, cfg, workload, metric, unit):
     del d_pot, d_vel
     pts = synth_points(n, w, h)
 
+    def note(msg):  # progress on stderr (CLUMPY_BENCH_VERBOSE=1)
+        if os.environ.get("CLUMPY_BENCH_VERBOSE") == "1":
+            print(f"[bench rank {rank} +{time.perf_counter() - t_start:.2f}s] {msg}", file=sys.stderr, flush=True)
+
     kind = os.environ.get("CLUMPY_MULTIGPU", "routed")
+    note("inputs ready")
     run = make_sharded(kind, ctx, pts, vel.numpy(), cfg["step_size"], cfg["kernel_size"], cfg["decay"], cfg["nframes"],
                        dist, device)
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    note("sharded run set up")
     run.step(W)
+    note("warm-up enqueued")
     dist.barrier()
     torch.cuda.synchronize()
+    note("warm-up done")
     launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -366,6 +376,7 @@ def bench_multi(args, cfg, workload, metric, unit):
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # slowest rank
     ms = float(ms.item())
+    note(f"timed region done: {ms / K:.4f} ms per frame")
     launches = ctx.launch_count() - launches0
     value = n * K / (ms * 1e-3)
 
@@ -378,6 +389,7 @@ def bench_multi(args, cfg, workload, metric, unit):
         kernel_ms = {"route": allt[:, 0].tolist(), "drain_incl_wait": allt[:, 1].tolist(), "composite": allt[:, 2].tolist(),
                      "points_per_rank": run.shard_sizes}
 
+    note(f"kernel profile done: {kernel_ms}")
     # e2e: every rank also copies its band of each recorded frame to pinned host memory
     y0, y1 = run.y0, run.y1
     host_band = [torch.empty((max(1, y1 - y0), w), dtype=torch.uint8).pin_memory() for _ in range(2)]
@@ -386,12 +398,18 @@ def bench_multi(args, cfg, workload, metric, unit):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     run2 = make_sharded(kind, ctx, pts, vel.numpy(), cfg["step_size"], cfg["kernel_size"], cfg["decay"], nrec, dist, device)
+    note("e2e: second run set up")
     run2.step(nrec)
+    note("e2e: warm-up frames enqueued")
     for f in range(nrec):
         run2.step(1)
         if y1 > y0:
             host_band[f & 1][:y1 - y0].copy_(run2.band_image(), non_blocking=True)
+        if f % 50 == 0:
+            note(f"e2e: recorded frame {f} enqueued")
+    note("e2e: all frames enqueued")
     torch.cuda.synchronize()
+    note(f"e2e: device idle, fence time-outs so far: {run2.adv.route_errors() if kind == 'routed' else 0}")
     dist.barrier()
     dt = torch.tensor([time.perf_counter() - t0], device=device)
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)

@@ -37,10 +37,10 @@ class RanksOnOneGpu:
         self.rows = [a.owned_rows() for a in self.advs]
 
     def step(self, count=1):
-        # one frame at a time: a rank's drain waits (bounded) for the epochs of ranks enqueued after it
-        for _ in range(count):
-            for a in self.advs:
-                a.route_steps(1)
+        # every rank enqueues the same `count` frames (one route launch covers up to 4 of them); a
+        # rank's drains wait (bounded) for the epochs of the ranks enqueued after it
+        for a in self.advs:
+            a.route_steps(count)
 
     def image(self):
         img = np.zeros((self.h, self.w), np.uint8)
@@ -69,7 +69,7 @@ def _field(oracle_mod, w, h, seed=8):
     return vel
 
 
-@pytest.mark.parametrize("overlap", [False, True])
+@pytest.mark.parametrize("overlap,chunk", [(False, 1), (True, 1), (True, 4), (False, 3)])
 @pytest.mark.parametrize("world,w,h,n,k,decay,nframes,step", [
     (2, 320, 200, 70001, 3, 0.98, 6, 35.0),
     (3, 256, 160, 30000, 1, 0.9, 5, 40.0),
@@ -78,16 +78,18 @@ def _field(oracle_mod, w, h, seed=8):
     (8, 300, 520, 90000, 3, 0.97, 5, 90.0),     # eight bands, fast field: many points change band
     (2, 128, 96, 5000, 3, 0.0, 3, 25.0),        # decay 0: warm-up frames do not splat at all
 ])
-def test_ranks_on_one_gpu_match_oracle(oracle_mod, monkeypatch, overlap, world, w, h, n, k, decay, nframes, step):
+def test_ranks_on_one_gpu_match_oracle(oracle_mod, monkeypatch, overlap, chunk, world, w, h, n, k, decay, nframes, step):
     vel = _field(oracle_mod, w, h)
     # a cloud that also has points outside the image on every side
     pts = ((np.random.default_rng(21).random((n, 2)) * 1.04 - 0.02) * [w, h]).astype(np.float32)
     run = RanksOnOneGpu(world, pts, vel, step, k, decay, nframes, monkeypatch, overlap)
     ref = oracle_mod.Advect(pts, vel, step, k, decay, nframes)
     try:
-        for s in range(2 * nframes):
-            run.step()
-            ref.step()
+        for s in range(0, 2 * nframes, chunk):
+            todo = min(chunk, 2 * nframes - s)  # groups of frames: fused route launches, crossing the warm-up boundary
+            run.step(todo)
+            for _ in range(todo):
+                ref.step()
             assert np.array_equal(run.points().view(np.uint32), ref.points().view(np.uint32)), f"trajectories differ at frame {s}"
             frac, worst = frame_agreement(run.image(), ref.image())
             assert frac >= 0.999, f"frame {s}: only {frac:.5f} of the pixels within 1 LSB (max {worst})"
