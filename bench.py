@@ -47,6 +47,10 @@ WORKLOAD = ("C4: advect_points 16777216 uniform points (default_rng(0)) on 8192x
             "kernel 3, step 240, decay 0.99, nframes 1000")
 ALGO_BYTES_PER_POINT_STEP = 28  # 8 R + 8 W position, 8 R velocity texel, 4 R reset offset
 ALGO_BYTES_PER_PIXEL_FRAME = 2  # u8 framebuffer read + write
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE advect_kernel launch on this workload, from the
+# round-1 `ncu --set full` capture (profiles/r1_ncu_full_summary.txt: 505.756 MB read + 159.334 MB
+# written).  Not measured by this script: a number taken under a profiler is never a bench value.
+NCU_TRAFFIC_BYTES_ADVECT_KERNEL_C4 = 505_756_000 + 159_334_000
 
 
 def measured_peaks():
@@ -294,7 +298,8 @@ def run_ours(args):
                         f"{e2e_steps} simulation frames, D2H of {nrec} recorded frames"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "advect_kernel", "achieved": achieved, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_ADVECT_KERNEL_C4,
+                     "traffic_source": "ncu --set full, profiles/r1_ncu_full_summary.txt (per launch, C4)",
                      "peak_source": peak_src, "kernel_ms": kms, "composite_ms": cms, "clear_ms": zms,
                      "algorithmic_bytes_per_launch": algo_bytes,
                      "step_frac": (algo_bytes + w * h * ALGO_BYTES_PER_PIXEL_FRAME) / (ms / K * 1e-3) / 1e9 / hbm_peak},

@@ -1200,12 +1200,18 @@ CLUMPY_API int clumpy_cuda_ipc_close(clumpy_cuda_ctx* ctx, void* dptr) {
     return CLUMPY_OK;
 }
 
+// One past the last image row this rank composites: its band's rows, and for the last rank the rest.
+static int route_last_row(const clumpy_advect* adv) {
+    const auto& rt = adv->route;
+    if (rt.rank == rt.world - 1) return (int)adv->height;
+    return std::max(0, std::min((int)adv->height, (rt.rank + 1) * rt.chunk - adv->geom.halo));
+}
+
 CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int world, uint32_t capacity,
                                               void** inbox_dev, size_t* inbox_bytes) {
     REQUIRE(adv && inbox_dev && inbox_bytes, "null argument");
     REQUIRE(world >= 1 && world <= ROUTE_MAX_WORLD && rank >= 0 && rank < world, "bad rank / world size");
     REQUIRE(adv->cell_mode == CELL_F16 || adv->cell_mode == CELL_U32, "routing needs count-only cells (f16 or u32)");
-    REQUIRE(adv->geom.rows % world == 0, "counter rows must be a multiple of the world size (CLUMPY_CUDA_CELL_ROWS_MULTIPLE)");
     REQUIRE(capacity >= adv->npts, "capacity must be at least the largest shard");
     REQUIRE(!adv->route.on, "routing already set up");
     clumpy_cuda_ctx* ctx = adv->ctx;
@@ -1213,7 +1219,12 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     auto& rt = adv->route;
     rt.rank = rank; rt.world = world;
     rt.nregion = std::max<uint32_t>(ceil_div(capacity, ROUTE_BLOCK), 1u); // one region per CTA of the largest shard
-    rt.chunk = adv->geom.rows / world;
+    // Bands of `chunk` padded rows, whole 16-row composite tiles, chosen from the IMAGE height so that
+    // for a uniform cloud they coincide with the home-row strips of the shards (4096 rows on 8 ranks: 512
+    // each, not the 528 that an even split of the 4098 padded rows would give: with those, rank 7 would
+    // start with a fifth of its points in rank 6's band).  The last band also takes whatever is left
+    // (the 2 * halo padding rows), which fits in the 32 slack rows of its band buffer.
+    rt.chunk = (int)round_up(ceil_div(adv->height, (uint32_t)world), 16);
     REQUIRE(world == 1 || rt.chunk >= 2 * adv->geom.halo, "bands thinner than the sprite are not supported");
     rt.fuse = ROUTE_MAX_FUSE;
     if (const char* fz = getenv("CLUMPY_ROUTE_FUSE")) rt.fuse = std::min(std::max(atoi(fz), 1), ROUTE_MAX_FUSE);
@@ -1269,7 +1280,7 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
                                                                          rt.band, rt.band_cells, band1, (uint32_t)(rt.band_bytes / 16));
         CK_LAUNCH(ctx);
         const int h = adv->geom.halo, lo = rank * rt.chunk;
-        const int y0 = std::max(0, lo - h), y1 = std::min((int)adv->height, lo + rt.chunk - h);
+        const int y0 = std::max(0, lo - h), y1 = route_last_row(adv);
         if (y1 > y0) {
             const char* cells = reinterpret_cast<const char*>(rt.band) + (size_t)(y0 - (lo - h)) * adv->geom.pitch * cell_bytes;
             int rc = composite_rows_impl(adv, cells, (uint32_t)y0, (uint32_t)(y1 - y0));
@@ -1448,7 +1459,7 @@ static int route_receive(clumpy_advect* adv, bool fenced, uint32_t epoch, cudaEv
         if (ev) CK(cudaEventRecord(ev[2], main_stream));
         // image rows this rank owns: those whose window of padded rows lies in chunk + halos
         const int lo = rt.rank * rt.chunk;
-        const int y0 = std::max(0, lo - h), y1 = std::min((int)adv->height, lo + rt.chunk - h);
+        const int y0 = std::max(0, lo - h), y1 = route_last_row(adv);
         if (y1 > y0) {
             if (overlap) CK(cudaStreamWaitEvent(side2, rt.drained[cur], 0));
             const size_t cell_bytes = adv->cell_mode == CELL_F16 ? 2 : 4;
@@ -1577,7 +1588,7 @@ CLUMPY_API int clumpy_cuda_advect_route_errors(clumpy_advect* adv, uint32_t* err
 CLUMPY_API int clumpy_cuda_advect_owned_rows(clumpy_advect* adv, uint32_t* row0, uint32_t* nrows) {
     REQUIRE(adv && row0 && nrows && adv->route.on, "routing is not set up");
     const int h = adv->geom.halo, lo = adv->route.rank * adv->route.chunk;
-    const int y0 = std::max(0, lo - h), y1 = std::min((int)adv->height, lo + adv->route.chunk - h);
+    const int y0 = std::max(0, lo - h), y1 = route_last_row(adv);
     *row0 = (uint32_t)y0;
     *nrows = (uint32_t)std::max(0, y1 - y0);
     return CLUMPY_OK;

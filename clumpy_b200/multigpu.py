@@ -359,7 +359,8 @@ def bench_multi(args, cfg, workload, metric, unit):
     note("inputs ready")
     run = make_sharded(kind, ctx, pts, vel.numpy(), cfg["step_size"], cfg["kernel_size"], cfg["decay"], cfg["nframes"],
                        dist, device)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # CLUMPY_BENCH_NO_CLOCKS=1 (A/B runs): nvidia-smi polling GPU 0 every 50 ms is not free for rank 0
+    sampler = ClockSampler(local_rank) if rank == 0 and os.environ.get("CLUMPY_BENCH_NO_CLOCKS") != "1" else None
     note("sharded run set up")
     run.step(W)
     note("warm-up enqueued")
@@ -424,13 +425,18 @@ def bench_multi(args, cfg, workload, metric, unit):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32+u8", "data": "synthetic",
             "config": {"workload": workload, "frames_per_s": K / (ms * 1e-3),
-                       "parallelism": (f"points sharded x{world}, field replicated, counter image distributed by row "
-                                       "bands; each advect kernel stores its points' cell indices into the band owners' "
-                                       "inboxes through peer memory (NVLink), all-gather of the entry counts as the "
-                                       "frame fence, band composite per rank") if kind == "routed" else
+                       "parallelism": (f"points sharded x{world} by home row, field replicated, counter image distributed by "
+                                       "row bands; a rank's route kernel (up to 4 frames per launch) counts the points "
+                                       "that land in its own band directly and stores the others' cell indices into the "
+                                       "band owners' inboxes through peer memory (NVLink); device-side frame fence (epoch "
+                                       "flags in peer memory); drain + band composite per rank on side streams; no "
+                                       "collective on the data path") if kind == "routed" else
                                       (f"points sharded x{world}, field replicated, per-frame NCCL reduce-scatter of the "
                                        "f16 counter image by row bands + halo all-gather, band composite per rank"),
-                       "l2": "inputs larger than L2 (field 268 MB per GPU)"},
+                       "l2": "inputs larger than L2, no flush: per rank and ring period (8 frames) the frames touch positions + "
+                             "phases (21 MB at 8 ranks), the rank's part of the field (~35-60 MB), 8 band buffers "
+                             "(8 x 8.6 MB), the image band and the inbox slots -- ~160 MB at 8 ranks, more with fewer "
+                             "ranks -- against 126 MB of L2"},
             "clocks": clocks,
             "e2e": {"value": n * e2e_steps / dt, "unit": unit,
                     "h2d_bytes_per_step": (n * 12 + world * w * h * 8) / e2e_steps, "d2h_bytes_per_step": nrec * w * h / e2e_steps,
