@@ -166,22 +166,27 @@ int clumpy_cuda_advect_composite_rows(clumpy_advect* adv, const void* cells_dev,
 int clumpy_cuda_advect_finish_frame(clumpy_advect* adv);
 
 /* ---- multi-GPU with the exchange fused into the advect kernel -----------------------------------
- * The counter image is distributed by bands of padded rows (band g on GPU g) and never exists as a
- * whole.  clumpy_cuda_advect_route advects this GPU's points and stores each point's cell index
- * (4 bytes) straight into the inbox of the GPU that owns the cell's band -- and of the neighbouring
- * band when the row lies within the sprite's reach of the edge -- through peer-mapped memory
- * (NVLink / NVSwitch stores from inside the kernel).  The per-destination entry counts it leaves in
- * *counts_dev (world x uint32) are all-gathered by the caller (that collective is also the frame
- * fence); clumpy_cuda_advect_drain then counts this GPU's inbox into its band buffer, composites the
- * image rows it owns, clears the band and advances the frame.  Inboxes are double-buffered by frame
- * parity, so a GPU may already route frame s+1 while a peer still drains frame s.
+ * Replaces the loop of commands/advect_points.cc:139-176 when the points of one run are spread over
+ * several GPUs (points advect independently, :144-153; the splat, splat_points.cc:118-161, is the one
+ * thing they share).  The counter image is distributed by bands of chunk = round_up(ceil(H / world), 16)
+ * padded rows (band g on GPU g, the last band also takes the padding rows) and never exists as a
+ * whole.  The route kernel advects this GPU's points, counts the ones that land in its own band
+ * straight into its band buffer and stores every other point's cell index (4 bytes) into the inbox of
+ * the GPU that owns the cell's band -- and of the neighbouring band when the row lies within the
+ * sprite's reach of the edge -- through peer-mapped memory (NVLink / NVSwitch stores from inside the
+ * kernel).  A drain kernel counts the inbox into the band buffer; the band's image rows are then
+ * composited as on one GPU.  Best with shards by HOME ROW (clumpy_b200/multigpu.py shard_indices):
+ * most points then never leave their GPU.
  *
- *   set-up:   route_begin (allocates this rank's inbox; export it with clumpy_cuda_ipc_export,
- *             exchange the handles, open the peers' with clumpy_cuda_ipc_open) -> route_peers
- *   a frame:  route -> all-gather(counts) -> drain(counts_all)        counts_all[s*world + d]
+ *   set-up:   advect_begin with this rank's points (count-only cells: CLUMPY_CUDA_CELLS=f16|u32)
+ *             -> route_begin (allocates this rank's inbox; export it with clumpy_cuda_ipc_export,
+ *             exchange the handles, open the peers' with clumpy_cuda_ipc_open -- or, for several
+ *             ranks on one GPU in one process, pass the device pointers themselves) -> route_peers
+ *   frames:   route_steps(count)                       fence on the device, nothing else to call
+ *        or:  route -> any collective on the context's stream that all ranks enter -> drain
  *
- * `capacity` = entries per (source, destination) segment, at least the largest shard's point count.
- * Needs count-only cells and CLUMPY_CUDA_CELL_ROWS_MULTIPLE = 16 * world at advect_begin. */
+ * `capacity` = point count of the largest shard (the same value on every rank).  Inboxes, band
+ * buffers and fence tickets are rings of 8 frames, so a GPU may run a few frames ahead of a peer. */
 #define CLUMPY_IPC_HANDLE_BYTES 64
 int clumpy_cuda_ipc_export(clumpy_cuda_ctx* ctx, const void* dptr, void* handle64);
 int clumpy_cuda_ipc_open(clumpy_cuda_ctx* ctx, const void* handle64, void** dptr);
@@ -193,12 +198,15 @@ int clumpy_cuda_advect_route(clumpy_advect* adv, void** counts_dev);
 int clumpy_cuda_advect_drain(clumpy_advect* adv, const uint32_t* counts_all_dev);
 int clumpy_cuda_advect_owned_rows(clumpy_advect* adv, uint32_t* row0, uint32_t* nrows);
 
-/* The same frames with the fence on the DEVICE instead of a host-side collective: after its route
- * kernel every rank stores its per-destination counts and the frame's epoch into the tail of each
- * peer's inbox (a one-warp kernel, ordered after the route kernel by the stream), and the drain kernel
- * waits for every source's epoch before reading its segment (bounded wait: ~2 s, then the segment is
- * skipped and counted in route_errors, so a dead peer cannot hang the GPU).  `count` frames are
- * enqueued by one call, with no host synchronisation and no NCCL on the data path. */
+/* `count` frames with the fence on the DEVICE: the CTAs of the route kernel that stored into a peer's
+ * inbox fence those stores and add themselves to the frame's ticket; an extra last CTA waits for the
+ * ticket and stores the frame's epoch into a flag per source in every peer's memory; the drain kernel
+ * waits for every source's epoch before it reads that source's entries (bounded wait: ~2 s, then the
+ * source is skipped and counted in route_errors, so a dead peer cannot hang the GPU).  One route
+ * launch covers up to 4 frames; drains and composites run on side streams.  All `count` frames are
+ * enqueued by the one call, with no host synchronisation and no NCCL on the data path.
+ * clumpy_cuda_advect_route / _drain are the one-frame variant for callers that fence themselves
+ * (counts_dev / counts_all_dev are kept for source compatibility: world zeros / ignored). */
 int clumpy_cuda_advect_route_steps(clumpy_advect* adv, uint32_t count);
 /* route_steps with CUDA events around every kernel: mean device time per frame (ms) of the route
  * kernel, the drain kernel (includes the wait for the slowest peer) and the band composite.  Every
