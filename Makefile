@@ -12,7 +12,7 @@ NVFLAGS  := $(ARCH) -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -Iinclude 
             -Xcompiler -fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function $(EXTRA_NVFLAGS)
 CSRC     := clumpy_b200/csrc
 CUFILES  := $(CSRC)/context.cu $(CSRC)/simplex.cu $(CSRC)/curl.cu $(CSRC)/splat.cu \
-            $(CSRC)/composite_dense.cu $(CSRC)/composite_exact.cu $(CSRC)/advect.cu
+            $(CSRC)/composite_dense.cu $(CSRC)/composite_exact.cu $(CSRC)/advect.cu $(CSRC)/producers.cu
 CUOBJS   := $(CUFILES:.cu=.o)
 LIB      := clumpy_b200/libclumpy_cuda.so
 HOST     := clumpy_b200/host
@@ -32,7 +32,7 @@ $(LIB): $(CUOBJS)
 cli: $(CLI)
 
 $(CLI): $(CLISRC) $(HOST)/clumpy_command.hh $(HOST)/npy.hh $(LIB)
-	$(CXX) -std=c++17 -O2 -Wall -Iinclude -I$(HOST) -o $@ $(CLISRC) -Lclumpy_b200 -lclumpy_cuda \
+	$(CXX) -std=c++17 -O2 -ffp-contract=off -Wall -Iinclude -I$(HOST) -o $@ $(CLISRC) -Lclumpy_b200 -lclumpy_cuda \
 	  -Wl,-rpath,'$$ORIGIN' -lpthread
 
 oracle:

@@ -75,6 +75,11 @@ SIGNATURES = {
     "clumpy_cuda_advect_owned_rows": (C.c_int, [C.c_void_p, _u32p, _u32p]),
     "clumpy_cuda_advect_route_steps": (C.c_int, [C.c_void_p, C.c_uint32]),
     "clumpy_cuda_advect_route_errors": (C.c_int, [C.c_void_p, _u32p]),
+    "clumpy_cuda_pendulum_phase": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "clumpy_cuda_pendulum_phase_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float,
+                                                 C.c_float, C.c_float, C.c_void_p]),
+    "clumpy_cuda_cull_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
+                                          C.c_void_p, _u32p]),
     "clumpy_cuda_advect_route_profile": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _f32p, _f32p]),
     "clumpy_cuda_advect_simframe": (C.c_int, [C.c_void_p, _u32p]),
     "clumpy_cuda_advect_frame_async": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -219,6 +224,29 @@ class Context:
         _check(lib().clumpy_cuda_curl_2d(self._h, _vp(src), w, h, _vp(out), C.byref(lo),
                                          C.byref(hi)))
         return out, lo.value, hi.value
+
+    def pendulum_phase(self, width, height, friction, scale_x, scale_y):
+        """-> (H, W, 2) float32   [clumpy pendulum_phase <WxH> <friction> <scale_x> <scale_y>]"""
+        out = np.empty((height, width, 2), np.float32)
+        _check(lib().clumpy_cuda_pendulum_phase(self._h, width, height, friction, scale_x, scale_y, _vp(out)))
+        return out
+
+    def pendulum_phase_dev(self, width, height, row0, nrows, friction, scale_x, scale_y, out_dev):
+        _check(lib().clumpy_cuda_pendulum_phase_dev(self._h, width, height, row0, nrows, friction, scale_x,
+                                                    scale_y, _vp(out_dev)))
+
+    def cull_points(self, pts, mask):
+        """(N, 2) points, (H, W) float32 mask -> the points over positive texels, in order   [clumpy cull_points]"""
+        pts, mask = _f32(pts), _f32(mask)
+        if pts.ndim != 2 or pts.shape[1] != 2:
+            raise ValueError("Input points must be 2D.")
+        if mask.ndim != 2:
+            raise ValueError("Input data has wrong shape.")
+        out = np.empty((max(len(pts), 1), 2), np.float32)
+        kept = C.c_uint32()
+        _check(lib().clumpy_cuda_cull_points(self._h, _vp(pts), len(pts), _vp(mask), mask.shape[1], mask.shape[0],
+                                             _vp(out), C.byref(kept)))
+        return out[:kept.value].copy()
 
     def splat_points(self, pts, width, height, img=None):
         """k=1, alpha=1 fast path of `clumpy splat_points` (splat_points.cc:108-116)."""

@@ -100,6 +100,30 @@ int clumpy_cuda_curl_2d_dev(clumpy_cuda_ctx* ctx, const float* src_dev, uint32_t
                             uint32_t nrows, const float* next_row_dev, float* dst_dev,
                             float* minval, float* maxval);
 
+/* ---- pendulum_phase, cull_points (the producers either side of the path) ------ */
+
+/* Replaces the loop of commands/pendulum_phase.cc:54-66: out_host (height, width, 2) float32 with
+ * texel(row, col) = (omega, -friction * omega - sin(theta)), theta = sx * (col / W - 0.5),
+ * omega = sy * (row / H - 0.5), sx = (float)(scale_x * M_PI / 0.5), sy = scale_y.  Bit-identical to
+ * the reference: the W values sinf(theta) and the H values omega are evaluated on the host exactly as
+ * the reference evaluates them per texel (same libm), the kernel combines them. */
+int clumpy_cuda_pendulum_phase(clumpy_cuda_ctx* ctx, uint32_t width, uint32_t height, float friction,
+                               float scale_x, float scale_y, float* out_host);
+
+/* Rows [row0, row0 + nrows) of the same field into device memory (rows are independent: the
+ * multi-GPU / fused-pipeline entry point). */
+int clumpy_cuda_pendulum_phase_dev(clumpy_cuda_ctx* ctx, uint32_t width, uint32_t height,
+                                   uint32_t row0, uint32_t nrows, float friction, float scale_x,
+                                   float scale_y, float* out_dev);
+
+/* Replaces cull_points() (commands/cull_points.cc:97-111): copies to out_host, in their original
+ * order, the points whose nearest mask texel is positive (coordinates converted float -> uint32_t as
+ * the reference does; outside the (height, width) float32 mask reads 0).  out_host holds up to npts
+ * points; *nkept receives how many were kept ("Removed {npts - nkept} points."). */
+int clumpy_cuda_cull_points(clumpy_cuda_ctx* ctx, const float* pts_host, uint32_t npts,
+                            const float* mask_host, uint32_t width, uint32_t height,
+                            float* out_host, uint32_t* nkept);
+
 /* ---- splat_points ---------------------------------------------------------------------- */
 
 /* Replaces splat_points() (commands/splat_points.cc:108-116): marks the texel under each point

@@ -56,6 +56,13 @@ def lib():
         L.oracle_advect_image.restype = _u8p
         L.oracle_advect_simframe.argtypes = [C.c_void_p]
         L.oracle_advect_simframe.restype = C.c_uint32
+        L.oracle_bridson_capacity.argtypes = [C.c_uint32, C.c_uint32, C.c_float]
+        L.oracle_bridson_capacity.restype = C.c_uint32
+        L.oracle_bridson_points.argtypes = [C.c_uint32, C.c_uint32, C.c_float, C.c_int, _f32p]
+        L.oracle_bridson_points.restype = C.c_uint32
+        L.oracle_pendulum_phase.argtypes = [C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, _f32p]
+        L.oracle_cull_points.argtypes = [_f32p, C.c_uint32, _f32p, C.c_uint32, C.c_uint32, _f32p]
+        L.oracle_cull_points.restype = C.c_uint32
         _LIB = L
     return _LIB
 
@@ -127,6 +134,30 @@ def age_offsets(nframes, npts):
     out = np.empty(npts, np.uint32)
     lib().oracle_age_offsets(nframes, npts, _ptr(out, _u32p))
     return out
+
+
+def bridson_points(width, height, radius, seed):
+    """-> (N, 2) float32   [bridson_points.cc:38-177]"""
+    cap = lib().oracle_bridson_capacity(width, height, radius)
+    out = np.empty((max(cap, 1), 2), np.float32)
+    n = lib().oracle_bridson_points(width, height, radius, int(seed), _ptr(out, _f32p))
+    return out[:n].copy()
+
+
+def pendulum_phase(width, height, friction, scalex, scaley):
+    """-> (H, W, 2) float32   [pendulum_phase.cc:38-71]"""
+    out = np.empty((height, width, 2), np.float32)
+    lib().oracle_pendulum_phase(width, height, friction, scalex, scaley, _ptr(out, _f32p))
+    return out
+
+
+def cull_points(pts, mask):
+    """(N, 2) points, (H, W) mask -> kept points in order   [cull_points.cc:97-111]"""
+    pts, mask = _f32(pts), _f32(mask)
+    h, w = mask.shape
+    out = np.empty((max(len(pts), 1), 2), np.float32)
+    n = lib().oracle_cull_points(_ptr(pts, _f32p), len(pts), _ptr(mask, _f32p), w, h, _ptr(out, _f32p))
+    return out[:n].copy()
 
 
 class Advect:

@@ -418,3 +418,151 @@ ORACLE_API int oracle_advect_step(oracle_advect_t* st)
 ORACLE_API const float* oracle_advect_points(const oracle_advect_t* st) { return st->pts; }
 ORACLE_API const uint8_t* oracle_advect_image(const oracle_advect_t* st) { return st->img; }
 ORACLE_API uint32_t oracle_advect_simframe(const oracle_advect_t* st) { return st->simframe; }
+
+/* =============================================================================================
+ * The producers either side of the path (SURVEY.md 8f "next": N1 bridson_points, N2 pendulum_phase,
+ * N4 cull_points).  Pinned like the rest: bit-identical to oracle/_ref/clumpy_ref on the fixtures of
+ * tests/golden/next_small.npz and on the C1 / C2 point lists and the C2 field (md5 in golden.json).
+ * ========================================================================================== */
+
+/* bridson_points.cc:60-66 -- integer hash that turns 0,1,2,... into random numbers */
+static uint32_t randhash(uint32_t seed)
+{
+    uint32_t i = (seed ^ 12345391u) * 2654435769u;
+    i ^= (i << 6) ^ (i >> 26);
+    i *= 2654435769u;
+    i += (i << 5) ^ (i >> 12);
+    return i;
+}
+
+/* bridson_points.cc:68-70: every operand is float; (float)UINT32_MAX rounds to 2^32 */
+static float randhashf(uint32_t seed, float a, float b)
+{
+    return (b - a) * (float)randhash(seed) / 4294967296.0f + a;
+}
+
+/* bridson_points.cc:72-86: a point of the annulus 1 < |r| <= 2 by rejection, scaled and moved */
+static void sample_annulus(float radius, float cx, float cy, int* seedptr, float* ox, float* oy)
+{
+    uint32_t seed = (uint32_t)*seedptr;
+    const float rscale = 1.0f / 4294967296.0f; /* 1.0f / UINT_MAX, the int converted to float */
+    float rx, ry;
+    for (;;) {
+        rx = 4 * rscale * (float)randhash(seed++) - 2;
+        ry = 4 * rscale * (float)randhash(seed++) - 2;
+        const float r2 = rx * rx + ry * ry;
+        if (r2 > 1 && r2 <= 4) break;
+    }
+    *seedptr = (int)seed;
+    *ox = rx * radius + cx;
+    *oy = ry * radius + cy;
+}
+
+static int clamp_i(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* bridson_points.cc:93-177 (generate_pts): Bridson's Poisson-disk sampling on a background grid of
+ * cell size r / sqrt(2), 30 attempts per active sample, all randomness from randhash(seed++).
+ * `out` must hold 2 * ceil(w / cell) * ceil(h / cell) floats (oracle_bridson_capacity); returns the
+ * number of points. */
+ORACLE_API uint32_t oracle_bridson_capacity(uint32_t w, uint32_t h, float radius)
+{
+    const float cellsize = radius / sqrtf(2);
+    const float invcell = 1.0f / cellsize;
+    const int ncols = (int)ceilf((float)w * invcell), nrows = (int)ceilf((float)h * invcell);
+    return (uint32_t)(ncols * nrows);
+}
+
+ORACLE_API uint32_t oracle_bridson_points(uint32_t w, uint32_t h, float radius, int seed, float* out)
+{
+    const float width = (float)w, height = (float)h;
+    const int maxattempts = 30;
+    const float rscale = 1.0f / 4294967296.0f;
+    const float r2 = radius * radius;
+    const float cellsize = radius / sqrtf(2);
+    const float invcell = 1.0f / cellsize;
+    const int ncols = (int)ceilf(width * invcell), nrows = (int)ceilf(height * invcell);
+    const int maxcol = ncols - 1, maxrow = nrows - 1, ncells = ncols * nrows;
+    if (ncells <= 0) return 0;
+    int* grid = (int*)malloc((size_t)ncells * sizeof(int));
+    int* actives = (int*)malloc((size_t)ncells * sizeof(int));
+    for (int i = 0; i < ncells; ++i) grid[i] = -1;
+    int nactives = 0, nsamples = 0;
+    float px = width * (float)randhash((uint32_t)seed++) * rscale;
+    float py = height * (float)randhash((uint32_t)seed++) * rscale;
+    grid[(int)(px * invcell) + ncols * (int)(py * invcell)] = actives[nactives++] = nsamples;
+    out[2 * nsamples] = px; out[2 * nsamples + 1] = py; ++nsamples;
+    while (nsamples < ncells) {
+        const float pick = randhashf((uint32_t)seed++, 0, (float)nactives);
+        const float cap = (float)nactives - 1.0f;
+        const int aindex = (int)(cap < pick ? cap : pick); /* min(a, b) = b < a ? b : a */
+        const int sindex = actives[aindex];
+        int found = 0;
+        for (int attempt = 0; attempt < maxattempts && !found; ++attempt) {
+            sample_annulus(radius, out[2 * sindex], out[2 * sindex + 1], &seed, &px, &py);
+            if (px < 0 || px >= width || py < 0 || py >= height) continue;
+            /* the window of grid cells within `radius`; its bounds pass through float on the way */
+            const float maxjx = (float)clamp_i((int)((px + radius) * invcell), 0, maxcol);
+            const float maxjy = (float)clamp_i((int)((py + radius) * invcell), 0, maxrow);
+            const float minjx = (float)clamp_i((int)((px - radius) * invcell), 0, maxcol);
+            const float minjy = (float)clamp_i((int)((py - radius) * invcell), 0, maxrow);
+            int reject = 0;
+            for (float jy = minjy; jy <= maxjy && !reject; jy++)
+                for (float jx = minjx; jx <= maxjx && !reject; jx++) {
+                    const int entry = grid[(int)jy * ncols + (int)jx];
+                    if (entry > -1 && entry != sindex) {
+                        const float dx = out[2 * entry] - px, dy = out[2 * entry + 1] - py;
+                        if (dx * dx + dy * dy < r2) reject = 1;
+                    }
+                }
+            if (reject) continue;
+            found = 1;
+        }
+        if (found) {
+            grid[(int)(px * invcell) + ncols * (int)(py * invcell)] = actives[nactives++] = nsamples;
+            out[2 * nsamples] = px; out[2 * nsamples + 1] = py; ++nsamples;
+        } else {
+            if (--nactives <= 0) break;
+            actives[aindex] = actives[nactives];
+        }
+    }
+    free(grid);
+    free(actives);
+    return (uint32_t)nsamples;
+}
+
+/* pendulum_phase.cc:38-71: out[row][col] = (omega, -friction * omega - g / L * sin(theta)) with
+ * theta = sx * (col / W - 0.5), omega = sy * (row / H - 0.5); the subtraction of 0.5 and the product
+ * with the scale run in double and round to float, sin is libm's sinf (the call resolves to it in the
+ * compiled reference), sx = (float)(scale_x * M_PI / 0.5). */
+ORACLE_API void oracle_pendulum_phase(uint32_t width, uint32_t height, float friction, float scalex,
+                                      float scaley, float* out)
+{
+    const float g = 1.0f, L = 1.0f;
+    const float gsx = (float)((double)scalex * M_PI / 0.5), gsy = scaley * 1;
+    for (uint32_t row = 0; row < height; ++row)
+        for (uint32_t col = 0; col < width; ++col) {
+            const float x = (float)((double)gsx * ((double)((float)col / (float)width) - 0.5));
+            const float y = (float)((double)gsy * ((double)((float)row / (float)height) - 0.5));
+            const float omega_dot = -friction * y - g / L * sinf(x);
+            out[2 * ((size_t)row * width + col)] = y;
+            out[2 * ((size_t)row * width + col) + 1] = omega_dot;
+        }
+}
+
+/* cull_points.cc:97-111: keep the points whose nearest mask texel (float -> uint32_t like texel_fetch,
+ * outside the image reads 0) is positive, in their original order; returns how many were kept. */
+ORACLE_API uint32_t oracle_cull_points(const float* pts, uint32_t npts, const float* mask,
+                                       uint32_t width, uint32_t height, float* out)
+{
+    uint32_t kept = 0;
+    for (uint32_t i = 0; i < npts; ++i) {
+        const uint32_t x = f2u32_x86(pts[2 * (size_t)i]), y = f2u32_x86(pts[2 * (size_t)i + 1]);
+        const float m = (x >= width || y >= height) ? 0.0f : mask[x + (size_t)width * y];
+        if (m > 0) {
+            out[2 * (size_t)kept] = pts[2 * (size_t)i];
+            out[2 * (size_t)kept + 1] = pts[2 * (size_t)i + 1];
+            ++kept;
+        }
+    }
+    return kept;
+}

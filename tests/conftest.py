@@ -31,6 +31,7 @@ def golden():
         "advect": dict(np.load(os.path.join(GOLDEN, "advect_small.npz"))),
         "splat": dict(np.load(os.path.join(GOLDEN, "splat_small.npz"))),
         "c1_pts": np.load(os.path.join(GOLDEN, "c1_pts.npy")),
+        "next": dict(np.load(os.path.join(GOLDEN, "next_small.npz"))),
     }
 
 

@@ -103,6 +103,35 @@ def main():
         meta[f"splat_{name}"] = {"k": int(k), "alpha": float(alpha), "stdout": out.strip()}
     np.savez_compressed(os.path.join(HERE, "splat_small.npz"), **spl)
 
+    # ---- the producers either side of the path: bridson_points, pendulum_phase, cull_points
+    nxt = {}
+    for name, (dims, radius, seed) in {"b0": ("200x100", "4", "3"), "b1": ("64x300", "2.5", "-7"),
+                                       "b2": ("37x19", "1", "5"), "b3": ("500x250", "10", "987")}.items():
+        out = run("bridson_points", dims, radius, seed, f"{name}.npy")
+        nxt[f"bridson_{name}"] = load(f"{name}.npy")
+        meta[f"bridson_{name}"] = {"args": [dims, radius, seed], "stdout": out.strip()}
+    for name, (dims, friction, sx, sy) in {"p0": ("64x48", "0.3", "0.7", "1.3"), "p1": ("333x17", "0.0", "3.0", "0.25"),
+                                           "p2": ("50x50", "0.01", "1.0", "5.0")}.items():
+        run("pendulum_phase", dims, friction, sx, sy, f"{name}.npy")
+        nxt[f"pendulum_{name}"] = load(f"{name}.npy")
+        meta[f"pendulum_{name}"] = {"args": [dims, friction, sx, sy]}
+    # C2 (README example6): the field and the point list by hash only (64 MB / 99 KB)
+    run("pendulum_phase", "4000x2000", "0.9", "2", "5", "field.npy")
+    run("bridson_points", "4000x2000", "20", "0", "pts_c2.npy")
+    meta["c2_md5"] = {"field.npy": md5(os.path.join(tmp, "field.npy")), "pts.npy": md5(os.path.join(tmp, "pts_c2.npy"))}
+    meta["c2_field_data_md5"] = hashlib.md5(load("field.npy").tobytes()).hexdigest()
+    meta["c2_pts_data_md5"] = hashlib.md5(load("pts_c2.npy").tobytes()).hexdigest()
+    rng = np.random.default_rng(1)
+    mask = rng.standard_normal((60, 100)).astype(np.float32)
+    cpts = ((rng.random((5000, 2)) * 1.2 - 0.1) * [100, 60]).astype(np.float32)
+    cpts[:5] = [[np.nan, 1], [1e12, 2], [-1e12, 3], [np.inf, 1], [3.999, 4.999]]
+    np.save(os.path.join(tmp, "mask.npy"), mask)
+    np.save(os.path.join(tmp, "cpts.npy"), cpts)
+    out = run("cull_points", "cpts.npy", "mask.npy", "culled.npy")
+    nxt["cull_mask"], nxt["cull_pts"], nxt["cull_out"] = mask, cpts, load("culled.npy")
+    meta["cull"] = {"stdout": out.strip()}
+    np.savez_compressed(os.path.join(HERE, "next_small.npz"), **nxt)
+
     # ---- scalar goldens SURVEY.md 8(c) lists ---------------------------------------------------
     meta["age_offsets_first10"] = {"240": [131, 142, 171, 202, 144, 205, 130, 203, 101, 149],
                                    "400": [219, 237, 286, 337, 241, 343, 217, 338, 169, 249],

@@ -381,3 +381,51 @@ def test_sharded_advect_world_of_one(ctx, oracle_mod, golden):
         dist.destroy_process_group()
         for v in ("CLUMPY_CUDA_CELLS", "CLUMPY_CUDA_OVERLAP", "CLUMPY_CUDA_CELL_ROWS_MULTIPLE"):
             os.environ.pop(v, None)
+
+
+# ---- the producers either side of the path ------------------------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,friction,sx,sy", [(64, 48, 0.3, 0.7, 1.3), (333, 17, 0.0, 3.0, 0.25), (500, 500, 0.01, 1.0, 5.0),
+                                                (1, 1, 0.5, 1.0, 1.0), (4001, 3, 0.9, 2.0, 5.0), (2, 1000, 1.5, 0.1, 9.0)])
+def test_pendulum_phase_bit_exact(ctx, oracle_mod, w, h, friction, sx, sy):
+    got = ctx.pendulum_phase(w, h, friction, sx, sy)
+    assert np.array_equal(got.view(np.uint32), oracle_mod.pendulum_phase(w, h, friction, sx, sy).view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_pendulum_phase_c2_field_and_row_bands(ctx, golden):
+    import hashlib
+    import torch
+    field = ctx.pendulum_phase(4000, 2000, 0.9, 2.0, 5.0)
+    assert hashlib.md5(field.tobytes()).hexdigest() == golden["meta"]["c2_field_data_md5"]
+    # rows are independent: bands written by the device entry point reproduce the whole field
+    w, h = 640, 101
+    whole = ctx.pendulum_phase(w, h, 0.2, 1.5, 2.5)
+    dev = torch.empty((h, w, 2), dtype=torch.float32, device="cuda")
+    for r0, n in ((0, 40), (40, 1), (41, 60)):
+        ctx.pendulum_phase_dev(w, h, r0, n, 0.2, 1.5, 2.5, dev[r0].data_ptr())
+    ctx.sync()
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy().view(np.uint32), whole.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_cull_points_golden_and_edge_cases(ctx, oracle_mod, golden):
+    nxt = golden["next"]
+    got = ctx.cull_points(nxt["cull_pts"], nxt["cull_mask"])
+    assert got.shape == nxt["cull_out"].shape and np.array_equal(got.view(np.uint32), nxt["cull_out"].view(np.uint32))
+    rng = np.random.default_rng(3)
+    for (w, h, n) in [(1, 1, 10), (257, 33, 100001), (1000, 500, 1 << 20), (64, 64, 255), (64, 64, 256), (64, 64, 257)]:
+        mask = rng.standard_normal((h, w)).astype(np.float32)
+        pts = ((rng.random((n, 2)) * 1.3 - 0.15) * [w, h]).astype(np.float32)
+        pts[:4] = [[np.nan, 0], [-0.5, 0.5], [4e9, 1], [-1e30, 2]]
+        ref = oracle_mod.cull_points(pts, mask)
+        got = ctx.cull_points(pts, mask)
+        assert got.shape == ref.shape and np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (w, h, n)
+    # nothing kept / everything kept / no points at all
+    ones = np.ones((8, 8), np.float32)
+    inside = (rng.random((1000, 2)) * 8).astype(np.float32)
+    assert len(ctx.cull_points(inside, -ones)) == 0
+    assert np.array_equal(ctx.cull_points(inside, ones), inside)
+    assert ctx.cull_points(np.zeros((0, 2), np.float32), ones).shape == (0, 2)

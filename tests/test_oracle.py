@@ -7,6 +7,8 @@ operation order and the build forbids FMA contraction.
 """
 import hashlib
 
+import os
+
 import numpy as np
 import pytest
 
@@ -130,3 +132,65 @@ def test_against_live_reference(oracle_mod, tmp_path):
         mine = np.array([oracle_mod.simplex2(perm, x, y) for x, y in xy[:3000]])
         theirs = oracle_mod.ref_simplex2(seed, xy[:3000])
         assert np.array_equal(mine, theirs)
+
+
+# ---- the producers either side of the path: oracle vs the compiled reference ----------
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("name", ["b0", "b1", "b2", "b3"])
+def test_bridson_points_golden(oracle_mod, golden, name):
+    dims, radius, seed = golden["meta"][f"bridson_{name}"]["args"]
+    w, h = (int(v) for v in dims.split("x"))
+    ref = golden["next"][f"bridson_{name}"]
+    mine = oracle_mod.bridson_points(w, h, float(radius), int(seed))
+    assert mine.shape == ref.shape
+    assert golden["meta"][f"bridson_{name}"]["stdout"] == f"Generated {len(ref)} points."
+    assert np.array_equal(_bits(mine), _bits(ref))
+
+
+def test_bridson_points_c1_and_c2_lists(oracle_mod, golden):
+    """The point lists of README example5 / example6 (bridson_points 1000x500 5 0 and 4000x2000 20 0)."""
+    import hashlib
+    c1 = oracle_mod.bridson_points(1000, 500, 5.0, 0)
+    assert np.array_equal(_bits(c1), _bits(golden["c1_pts"])) and len(c1) == 12392
+    c2 = oracle_mod.bridson_points(4000, 2000, 20.0, 0)
+    assert hashlib.md5(c2.tobytes()).hexdigest() == golden["meta"]["c2_pts_data_md5"] and len(c2) == 12392
+
+
+@pytest.mark.parametrize("name", ["p0", "p1", "p2"])
+def test_pendulum_phase_golden(oracle_mod, golden, name):
+    dims, friction, sx, sy = golden["meta"][f"pendulum_{name}"]["args"]
+    w, h = (int(v) for v in dims.split("x"))
+    mine = oracle_mod.pendulum_phase(w, h, float(friction), float(sx), float(sy))
+    assert np.array_equal(_bits(mine), _bits(golden["next"][f"pendulum_{name}"]))
+
+
+def test_pendulum_phase_c2_field(oracle_mod, golden):
+    import hashlib
+    field = oracle_mod.pendulum_phase(4000, 2000, 0.9, 2.0, 5.0)
+    assert hashlib.md5(field.tobytes()).hexdigest() == golden["meta"]["c2_field_data_md5"]
+    assert golden["meta"]["c2_md5"]["field.npy"] == "c6107b1fa21605d0a8c920f02b6e6710"  # SURVEY.md 8(c)
+
+
+def test_cull_points_golden(oracle_mod, golden):
+    nxt = golden["next"]
+    mine = oracle_mod.cull_points(nxt["cull_pts"], nxt["cull_mask"])
+    assert np.array_equal(_bits(mine), _bits(nxt["cull_out"]))
+    assert golden["meta"]["cull"]["stdout"] == f"Removed {len(nxt['cull_pts']) - len(mine)} points."
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/commands/bridson_points.cc"), reason="needs the reference sources")
+def test_producers_against_the_compiled_reference(oracle_mod, tmp_path):
+    """Where the reference can be run (the build container): more shapes than the committed fixtures."""
+    if not oracle_mod.have_ref():
+        pytest.skip("oracle/_ref not built")
+    run = lambda *a: oracle_mod.ref_cli(*a, cwd=str(tmp_path))
+    for (w, h, r, seed) in [(300, 300, 0.8, 11), (128, 32, 3.3, 2), (90, 90, 6.0, -3)]:
+        run("bridson_points", f"{w}x{h}", str(r), str(seed), "p.npy")
+        assert np.array_equal(_bits(np.load(tmp_path / "p.npy")), _bits(oracle_mod.bridson_points(w, h, r, seed)))
+    for (w, h, fr, sx, sy) in [(500, 500, 0.01, 1.0, 5.0), (77, 200, 1.5, 0.1, 9.0)]:
+        run("pendulum_phase", f"{w}x{h}", str(fr), str(sx), str(sy), "f.npy")
+        assert np.array_equal(_bits(np.load(tmp_path / "f.npy")), _bits(oracle_mod.pendulum_phase(w, h, fr, sx, sy)))
