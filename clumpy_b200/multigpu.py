@@ -54,6 +54,42 @@ def shard_indices(pts, height, world, rank, how="home_rows"):
     return np.nonzero((row >= edges[rank]) & (row < edges[rank + 1]))[0]
 
 
+def field_rows(height, world, rank):
+    """Rows [r0, r1) of a (height, width) field that rank `rank` generates: equal bands (the last ranks
+    one row shorter when `world` does not divide `height`)."""
+    return shard_range(height, world, rank)
+
+
+def sharded_simplex_curl(ctx, width, height, amplitude, frequency, seed, dist, device):
+    """generate_simplex -> curl_2d with the ROWS sharded across the ranks (BASELINE configs[2]): rank r
+    evaluates the potential on its band plus the one row below it -- curl_2d is a forward difference
+    (curl_2d.cc:57-71), so the halo is one row in one direction, and recomputing it costs 1/band of the
+    band instead of a point-to-point exchange -- curls the band, and the velocity bands are all-gathered
+    so that every rank ends up with the whole field (advect_points replicates it).  Returns a
+    (height, width, 2) float32 torch tensor on `device`, bit-identical to the single-GPU field."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    r0, r1 = field_rows(height, world, rank)
+    halo = 1 if r1 < height else 0
+    pot = torch.empty((max(r1 - r0 + halo, 1), width), dtype=torch.float32, device=device)
+    band = torch.zeros((max(r1 - r0, 1), width, 2), dtype=torch.float32, device=device)
+    if r1 > r0:
+        ctx.generate_simplex_dev(width, height, r0, r1 - r0 + halo, amplitude, frequency, seed, pot.data_ptr())
+        ctx.curl_2d_dev(pot.data_ptr(), width, r1 - r0, pot[r1 - r0].data_ptr() if halo else None, band.data_ptr())
+    if world == 1:
+        return band[:height]
+    # bands differ by at most one row: gather them padded to the longest
+    longest = max(field_rows(height, world, r)[1] - field_rows(height, world, r)[0] for r in range(world))
+    padded = torch.zeros((longest, width, 2), dtype=torch.float32, device=device)
+    padded[:r1 - r0].copy_(band[:r1 - r0])
+    everything = torch.empty((world, longest, width, 2), dtype=torch.float32, device=device)
+    if everything.is_cuda:
+        dist.all_gather_into_tensor(everything, padded)
+    else:
+        dist.all_gather(list(everything.unbind(0)), padded)
+    return torch.cat([everything[r, :field_rows(height, world, r)[1] - field_rows(height, world, r)[0]] for r in range(world)])
+
+
 class BandPlan:
     """Row bands of the padded counter image (rows_alloc = world * chunk rows)."""
 
@@ -228,8 +264,8 @@ class RoutedAdvect:
         how = os.environ.get("CLUMPY_MULTIGPU_SHARD", "home_rows")
         self.indices = shard_indices(pts, self.h_img, self.world, self.rank, how)
         offsets = clumpy_b200.age_offsets(nframes, n)[self.indices]  # offsets follow the GLOBAL point index
-        os.environ["CLUMPY_CUDA_CELLS"] = "f16" if kernel_size <= 3 else "u32"
-        os.environ["CLUMPY_CUDA_CELL_ROWS_MULTIPLE"] = str(CELL_ROW_MULTIPLE * self.world)
+        os.environ["CLUMPY_CUDA_CELLS"] = "f16" if kernel_size <= 3 else "u32"  # count-only cells
+        os.environ.pop("CLUMPY_CUDA_CELL_ROWS_MULTIPLE", None)  # (the dense variant's: bands here are the library's own)
         self.adv = ctx.advect(np.ascontiguousarray(pts[self.indices]), vel, step_size, kernel_size, decay, nframes,
                               age_offset=np.ascontiguousarray(offsets))
         sizes = torch.zeros(self.world, dtype=torch.int64, device=device)
@@ -339,16 +375,13 @@ def bench_multi(args, cfg, workload, metric, unit):
     K, W = args.steps, args.warmup
     hbm_peak, peak_src = measured_peaks()
 
-    # every rank builds the (replicated) field with the library's own kernels; points come from the
-    # same seeded recipe on every rank and are sliced by the sharded run
-    d_pot = torch.empty((h, w), dtype=torch.float32, device=device)
-    d_vel = torch.empty((h, w, 2), dtype=torch.float32, device=device)
-    ctx.generate_simplex_dev(w, h, 0, h, cfg["amplitude"], cfg["frequency"] / rows_div, cfg["seed"], d_pot.data_ptr())
-    ctx.curl_2d_dev(d_pot.data_ptr(), w, h, None, d_vel.data_ptr())
+    # points come from the same seeded recipe on every rank and are sliced by the sharded run
+    # the (replicated) field: simplex + curl row-sharded across the ranks, bands all-gathered over NCCL
+    d_vel = sharded_simplex_curl(ctx, w, h, cfg["amplitude"], cfg["frequency"] / rows_div, cfg["seed"], dist, device)
     vel = torch.empty((h, w, 2), dtype=torch.float32).pin_memory()
     vel.copy_(d_vel)
     torch.cuda.synchronize()
-    del d_pot, d_vel
+    del d_vel
     pts = synth_points(n, w, h)
 
     def note(msg):  # progress on stderr (CLUMPY_BENCH_VERBOSE=1)

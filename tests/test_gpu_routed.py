@@ -19,10 +19,10 @@ pytestmark = pytest.mark.gpu
 class RanksOnOneGpu:
     def __init__(self, world, pts, vel, step, k, decay, nframes, monkeypatch, overlap, shard="home_rows"):
         import clumpy_b200
-        from clumpy_b200.multigpu import CELL_ROW_MULTIPLE, shard_indices
+        from clumpy_b200.multigpu import shard_indices
         monkeypatch.setenv("CLUMPY_CUDA_CELLS", "f16" if k <= 3 else "u32")
         monkeypatch.setenv("CLUMPY_CUDA_OVERLAP", "1" if overlap else "0")
-        monkeypatch.setenv("CLUMPY_CUDA_CELL_ROWS_MULTIPLE", str(CELL_ROW_MULTIPLE * world))
+        monkeypatch.delenv("CLUMPY_CUDA_CELL_ROWS_MULTIPLE", raising=False)
         self.world, self.n, self.h, self.w = world, len(pts), vel.shape[0], vel.shape[1]
         offsets = clumpy_b200.age_offsets(nframes, len(pts))
         self.ctxs = [clumpy_b200.Context(0) for _ in range(world)]

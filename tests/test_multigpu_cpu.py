@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from clumpy_b200.multigpu import BandPlan, exchange_counts, shard_indices, shard_range
+from clumpy_b200.multigpu import BandPlan, exchange_counts, field_rows, shard_indices, shard_range
 
 
 def test_shard_range_covers_everything():
@@ -21,6 +21,14 @@ def test_shard_range_covers_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("height,world", [(4096, 8), (16384, 8), (37, 2), (5, 8), (1000, 3)])
+def test_field_rows_tile_the_image(height, world):
+    spans = [field_rows(height, world, r) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == height
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
 
 
 @pytest.mark.parametrize("how", ["home_rows", "index"])

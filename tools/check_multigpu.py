@@ -31,6 +31,20 @@ def main():
     torch.cuda.set_stream(stream)
     ctx = clumpy_b200.Context(local, stream.cuda_stream)
     ok = True
+    # generate_simplex -> curl_2d with the rows sharded across the ranks (+ all-gather of the velocity
+    # bands) must reproduce the single-GPU field bit for bit
+    from clumpy_b200.multigpu import sharded_simplex_curl
+    for (w, h, freq, seed) in [(512, 64, 8.0, 0), (300, 37, 20.0, 5), (2048, 1024, 8.0, 1)]:
+        got = sharded_simplex_curl(ctx, w, h, 1.0, freq, seed, dist, device).cpu().numpy()
+        pot = torch.empty((h, w), dtype=torch.float32, device=device)
+        whole = torch.empty((h, w, 2), dtype=torch.float32, device=device)
+        ctx.generate_simplex_dev(w, h, 0, h, 1.0, freq, seed, pot.data_ptr())
+        ctx.curl_2d_dev(pot.data_ptr(), w, h, None, whole.data_ptr())
+        torch.cuda.synchronize()
+        same = got.shape == (h, w, 2) and np.array_equal(got.view(np.uint32), whole.cpu().numpy().view(np.uint32))
+        ok = ok and same
+        if rank == 0:
+            print(f"[fields] simplex+curl {w}x{h} row-sharded x{dist.get_world_size()}: identical to one GPU = {same}")
     kinds = os.environ.get("CLUMPY_MULTIGPU_KINDS", "routed,dense").split(",")
     for kind in kinds:
       for (w, h, n, k, decay, nframes, step) in [(320, 200, 70001, 3, 0.98, 6, 35.0), (256, 160, 30000, 1, 0.9, 5, 40.0),
