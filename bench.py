@@ -51,6 +51,7 @@ ALGO_BYTES_PER_PIXEL_FRAME = 2  # u8 framebuffer read + write
 # round-1 `ncu --set full` capture (profiles/r1_ncu_full_summary.txt: 505.756 MB read + 159.334 MB
 # written).  Not measured by this script: a number taken under a profiler is never a bench value.
 NCU_TRAFFIC_BYTES_ADVECT_KERNEL_C4 = 505_756_000 + 159_334_000
+NCU_TRAFFIC_BYTES_FUSED_KERNEL_C4 = None  # filled in from the ncu capture of the 4-frame kernel (profiles/)
 
 
 def measured_peaks():
@@ -258,9 +259,13 @@ def run_ours(args):
     value = n * K / (ms * 1e-3)
 
     # ---- roofline: the dominant kernel alone (advect + count), same state, CUDA events --------
+    # The dominant kernel as the pipeline runs it: one launch advances `nf` frames (positions stay in
+    # registers), timed with CUDA events around the launch while the composites of the previous group
+    # share the GPU.  Then the one-frame kernels one by one, for reference.
+    launch_ms, nf = adv.profile_fused(40)
     kms, cms, zms = adv.profile(50)
-    algo_bytes = n * ALGO_BYTES_PER_POINT_STEP
-    achieved = algo_bytes / (kms * 1e-3) / 1e9
+    algo_bytes = n * ALGO_BYTES_PER_POINT_STEP * nf
+    achieved = algo_bytes / (launch_ms * 1e-3) / 1e9
     adv.close()
 
     # ---- e2e: whole command through the C ABI with host buffers ---------------------------------
@@ -297,12 +302,15 @@ def run_ours(args):
                 "what": "clumpy_cuda_advect_points with pinned host buffers: H2D of points+field+offsets, sort, "
                         f"{e2e_steps} simulation frames, D2H of {nrec} recorded frames"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "advect_kernel", "achieved": achieved, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_ADVECT_KERNEL_C4,
-                     "traffic_source": "ncu --set full, profiles/r1_ncu_full_summary.txt (per launch, C4)",
-                     "peak_source": peak_src, "kernel_ms": kms, "composite_ms": cms, "clear_ms": zms,
+        "roofline": {"bound": "hbm", "kernel": f"advect_fused_kernel ({nf} frames per launch)" if nf > 1 else "advect_kernel",
+                     "achieved": achieved, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": NCU_TRAFFIC_BYTES_FUSED_KERNEL_C4 if nf == 4 else (NCU_TRAFFIC_BYTES_ADVECT_KERNEL_C4 if nf == 1 else None),
+                     "traffic_source": "ncu --set full capture of this kernel on this workload, per launch (profiles/)",
+                     "peak_source": peak_src, "launch_ms": launch_ms, "frames_per_launch": nf,
+                     "one_frame_kernel_ms": kms, "composite_ms": cms, "clear_ms": zms,
                      "algorithmic_bytes_per_launch": algo_bytes,
-                     "step_frac": (algo_bytes + w * h * ALGO_BYTES_PER_PIXEL_FRAME) / (ms / K * 1e-3) / 1e9 / hbm_peak},
+                     "step_frac": (n * ALGO_BYTES_PER_POINT_STEP + w * h * ALGO_BYTES_PER_PIXEL_FRAME) / (ms / K * 1e-3) / 1e9 / hbm_peak},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

@@ -58,6 +58,7 @@ SIGNATURES = {
                                            C.c_int, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "clumpy_cuda_advect_step": (C.c_int, [C.c_void_p, C.c_uint32]),
     "clumpy_cuda_advect_profile": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _f32p, _f32p]),
+    "clumpy_cuda_advect_profile_fused": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _u32p]),
     "clumpy_cuda_advect_count": (C.c_int, [C.c_void_p]),
     "clumpy_cuda_advect_cells": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                            _u32p, _u32p, _u32p, _u32p]),
@@ -335,6 +336,12 @@ class Advect:
         a, c, z = C.c_float(), C.c_float(), C.c_float()
         _check(lib().clumpy_cuda_advect_profile(self._h, count, C.byref(a), C.byref(c), C.byref(z)))
         return a.value, c.value, z.value
+
+    def profile_fused(self, groups):
+        """-> (mean ms of one advect launch inside the running pipeline, frames per launch)."""
+        ms, nf = C.c_float(), C.c_uint32()
+        _check(lib().clumpy_cuda_advect_profile_fused(self._h, groups, C.byref(ms), C.byref(nf)))
+        return ms.value, nf.value
 
     @property
     def simframe(self):

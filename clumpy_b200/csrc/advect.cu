@@ -189,6 +189,74 @@ advect_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
     }
 }
 
+// Several frames per launch ("temporal blocking"): the positions are loaded once, advanced through `nf`
+// simulation frames in registers -- gather, Euler step, reset, count, each frame counting into the next
+// counter image of a ring -- and stored once.  Position and phase traffic (20 of the 28 algorithmic
+// bytes per point-step) is paid once per group instead of once per frame; the gathers and the counter
+// updates are what is left per frame.  Same arithmetic per frame as advect_kernel, so same results.
+template <bool WRAP, int MODE, typename OffT>
+__global__ void __launch_bounds__(ADVECT_THREADS)
+advect_fused_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
+                    const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
+                    uint32_t width, uint32_t height, float step, uint32_t phase0, uint32_t nframes, int nf,
+                    GeomDev g, uint32_t* __restrict__ hist0, size_t hist_stride_words, int slot0, int ring,
+                    uint32_t cap, int keep_cells) {
+    const uint32_t base = blockIdx.x * (ADVECT_THREADS * ADVECT_PTS) + threadIdx.x;
+    const uint64_t pol = g.keep_pos == 0 ? make_stream_policy() : make_normal_policy();
+    const uint64_t keep = keep_cells ? make_keep_policy() : make_normal_policy();
+    float2 p[ADVECT_PTS];
+    uint32_t off[ADVECT_PTS];
+    bool live[ADVECT_PTS]; // no early return: the byte-cell update below is warp-collective
+#pragma unroll
+    for (int k = 0; k < ADVECT_PTS; ++k) {
+        const uint32_t i = base + k * ADVECT_THREADS;
+        live[k] = i < npts;
+        p[k] = make_float2(0.f, 0.f);
+        off[k] = 0xFFFFFFFFu;
+        if (live[k]) {
+            p[k] = ld_stream_f2(pos + i, pol);
+            off[k] = ld_stream_off(offset + i, pol);
+        }
+    }
+    uint32_t phase = phase0;
+    for (int f = 0; f < nf; ++f) {
+        float2 v[ADVECT_PTS];
+#pragma unroll
+        for (int k = 0; k < ADVECT_PTS; ++k) { // nearest-texel fetch (advect_points.cc:23-37)
+            uint32_t x = f2u32_x86(p[k].x);
+            const uint32_t y = f2u32_x86(p[k].y);
+            if (WRAP) x = (width + (x % width)) % width;
+            v[k] = make_float2(0.f, 0.f);
+            if (live[k] && x < width && y < height) v[k] = __ldg(vel + ((size_t)y * width + x));
+        }
+#pragma unroll
+        for (int k = 0; k < ADVECT_PTS; ++k) {
+            // pt += step * v: rounded multiply, then rounded add (:146); reset AFTER the move (:147-152,166-170)
+            p[k] = make_float2(__fadd_rn(p[k].x, __fmul_rn(step, v[k].x)), __fadd_rn(p[k].y, __fmul_rn(step, v[k].y)));
+            if (off[k] == phase) p[k] = orig[base + k * ADVECT_THREADS];
+        }
+        phase = phase + 1u == nframes ? 0u : phase + 1u;
+        if (MODE != CELL_NONE) {
+            uint32_t* hist = hist0 + (size_t)((slot0 + f) % ring) * hist_stride_words;
+#pragma unroll
+            for (int k = 0; k < ADVECT_PTS; ++k) {
+                // splat_points.cc:143-144: centre texel by (int32_t) truncation
+                const long long at = live[k] ? hist_index<WRAP>(f2i32_x86(p[k].x), f2i32_x86(p[k].y), g) : -1;
+                if (MODE == CELL_X64) {
+                    const unsigned long long inc = ((unsigned long long)(base + k * ADVECT_THREADS) << 24) | 1ull;
+                    if (at >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(hist) + at, inc);
+                }
+                else if (MODE == CELL_U32) { if (at >= 0) atomicAdd(hist + at, 1u); }
+                else if (MODE == CELL_F16) { if (at >= 0) cell_add_f16(hist, at, keep); }
+                else cell_add_sat_u8(hist, at, cap);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ADVECT_PTS; ++k)
+        if (live[k]) st_stream_f2(pos + base + k * ADVECT_THREADS, p[k], pol);
+}
+
 // ---- multi-GPU: the splat exchange fused into the advect kernel ------------------------------------
 //
 // With G GPUs the counter image is distributed by bands of `chunk` padded rows (band d on GPU d) and
@@ -610,6 +678,8 @@ unpermute_kernel(const float2* __restrict__ pos, const uint32_t* __restrict__ pe
 
 using namespace clumpy;
 
+constexpr int HIST_RING = 8; // counter images in flight on the single-GPU path (see advect_group)
+
 struct clumpy_advect {
     clumpy_cuda_ctx* ctx = nullptr;
     uint32_t npts = 0, width = 0, height = 0, nframes = 0, simframe = 0;
@@ -628,7 +698,10 @@ struct clumpy_advect {
     SortGrid sort_grid = {};
     uint32_t regroup_every = 0, frames_since_regroup = 0; // 0: never regroup
     uint32_t* hist = nullptr; // the allocation: two counter images back to back (see CellMode)
-    uint32_t* hist_buf[2] = {nullptr, nullptr}; // frame s counts into hist_buf[cellbuf]
+    uint32_t* hist_buf[HIST_RING] = {}; // frame s counts into hist_buf[cellbuf]
+    int hist_ring = 2;        // counter images in the ring (HIST_RING, or 2 when they are too big)
+    int fuse = 1;             // simulation frames per advect launch (<= hist_ring / 2)
+    size_t hist_stride = 0;   // bytes between consecutive counter images
     int cellbuf = 0;
     int cell_mode = CELL_U32;
     size_t hist_bytes = 0;    // bytes of ONE counter image
@@ -663,8 +736,8 @@ struct clumpy_advect {
         uint32_t epoch_base = 0;
         bool loopback = false;       // CLUMPY_ROUTE_LOOPBACK=1: see route_begin
     } route;
-    bool clear_pending[2] = {false, false};
-    cudaEvent_t advected[2] = {nullptr, nullptr}, cleared[2] = {nullptr, nullptr}, side_done = nullptr;
+    bool clear_pending[HIST_RING] = {};
+    cudaEvent_t advected[2] = {nullptr, nullptr}, cleared[HIST_RING] = {}, side_done = nullptr;
     DenseTables dense;        // replay tables of the byte-counter path
     bool l2_window = false;   // an L2 persisting window for the counters is set on the stream
     uint8_t* img[2] = {nullptr, nullptr};
@@ -699,8 +772,8 @@ static void advect_release(clumpy_advect* a) {
     for (int b = 0; b < 2; ++b) {
         if (a->copy_done[b]) cudaEventDestroy(a->copy_done[b]);
         if (a->advected[b]) cudaEventDestroy(a->advected[b]);
-        if (a->cleared[b]) cudaEventDestroy(a->cleared[b]);
     }
+    for (int b = 0; b < HIST_RING; ++b) if (a->cleared[b]) cudaEventDestroy(a->cleared[b]);
     if (a->frame_ready) cudaEventDestroy(a->frame_ready);
     if (a->side_done) cudaEventDestroy(a->side_done);
     delete a;
@@ -836,6 +909,7 @@ static int advect_begin_impl(clumpy_advect* a, const float* pts_host, const floa
             if (a->dense.valid) a->cell_mode = (want == "u8") ? CELL_U8 : CELL_F16;
         }
     }
+    bool composite_cap_from_env = false;
     a->hist_bytes = a->cell_mode == CELL_U8 ? a->geom.cells()
                   : a->cell_mode == CELL_F16 ? a->geom.cells() * 2
                   : a->cell_mode == CELL_X64 ? a->geom.cells() * 8 : a->geom.bytes();
@@ -853,21 +927,35 @@ static int advect_begin_impl(clumpy_advect* a, const float* pts_host, const floa
         if (const char* kp = getenv("CLUMPY_CUDA_KEEP_POS")) a->keep_pos = kp[0] == '1';
         if (const char* cap = getenv("CLUMPY_CUDA_COMPOSITE_CTAS")) ctx->composite_ctas_per_sm = atoi(cap);
         else ctx->composite_ctas_per_sm = a->overlap ? 4 : 0;
+        composite_cap_from_env = getenv("CLUMPY_CUDA_COMPOSITE_CTAS") != nullptr;
     }
+    // A ring of counter images: one advect launch advances `fuse` frames, each counting into the next
+    // image of the ring, while the images of the previous group are still being composited and cleared
+    // on the side stream (so the ring holds two groups).  Very large images (> 512 MB each) fall back to
+    // two images and one frame per launch.  CLUMPY_CUDA_FUSE=<1..4> overrides (1 = the one-frame kernel).
     const size_t image_stride = round_up(a->hist_bytes, 256);
-    CK(cudaMalloc(&a->hist, 2 * image_stride));
-    a->hist_buf[0] = a->hist;
-    a->hist_buf[1] = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(a->hist) + image_stride);
+    a->hist_stride = image_stride;
+    a->hist_ring = image_stride <= (512ull << 20) ? HIST_RING : 2;
+    a->fuse = a->hist_ring / 2;
+    if (const char* fz = getenv("CLUMPY_CUDA_FUSE")) a->fuse = std::min(std::max(atoi(fz), 1), a->hist_ring / 2);
+    if (a->fuse == 1) a->hist_ring = 2;
+    // With several frames per advect launch the composites are the longer stage of the pipeline: give
+    // them 5 CTAs per SM instead of 4 (measured on C4: step 0.199 -> 0.177 ms, advect launch 0.417 ->
+    // 0.467 ms per 4 frames; 6 CTAs: 0.175 / 0.518, 8 CTAs: 0.179 / 0.609).
+    if (a->overlap && a->fuse > 1 && !composite_cap_from_env) ctx->composite_ctas_per_sm = 5;
+    CK(cudaMalloc(&a->hist, (size_t)a->hist_ring * image_stride));
+    for (int b = 0; b < a->hist_ring; ++b)
+        a->hist_buf[b] = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(a->hist) + (size_t)b * image_stride);
     CK(cudaMalloc(&a->img[0], npix));
     CK(cudaMalloc(&a->img[1], npix));
     for (int b = 0; b < 2; ++b) {
         CK(cudaEventCreateWithFlags(&a->copy_done[b], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&a->advected[b], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&a->cleared[b], cudaEventDisableTiming));
     }
+    for (int b = 0; b < HIST_RING; ++b) CK(cudaEventCreateWithFlags(&a->cleared[b], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&a->frame_ready, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&a->side_done, cudaEventDisableTiming));
-    CK(cudaMemsetAsync(a->hist, 0, 2 * image_stride, ctx->stream));
+    CK(cudaMemsetAsync(a->hist, 0, (size_t)a->hist_ring * image_stride, ctx->stream));
     // Optional (CLUMPY_CUDA_PERSIST=1): an L2 persisting window over the counters, which are touched
     // three times per frame while ~0.6 GB of streaming traffic passes by.  Measured on B200 it is a
     // wash for one 64 MB image (0.165 vs 0.178 ms advect) and a 2.3x LOSS for the two images of the
@@ -878,7 +966,7 @@ static int advect_begin_impl(clumpy_advect* a, const float* pts_host, const floa
         cudaDeviceProp prop;
         if ((a->cell_mode == CELL_U8 || a->cell_mode == CELL_F16) && (on && on[0] == '1') &&
             cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0) {
-            const size_t window = std::min<size_t>(2 * image_stride, (size_t)prop.accessPolicyMaxWindowSize);
+            const size_t window = std::min<size_t>((size_t)a->hist_ring * image_stride, (size_t)prop.accessPolicyMaxWindowSize);
             const size_t want = std::min<size_t>(window, (size_t)prop.persistingL2CacheMaxSize);
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
             cudaStreamAttrValue attr = {};
@@ -955,105 +1043,136 @@ CLUMPY_API int clumpy_cuda_advect_begin(clumpy_cuda_ctx* ctx, const float* pts_h
 }
 
 template <bool WRAP, int MODE, typename OffT>
-static void launch_advect_t(clumpy_advect* a, uint32_t phase) {
+static void launch_advect_t(clumpy_advect* a, uint32_t phase, int nf) {
     const uint32_t grid = ceil_div(a->npts, ADVECT_THREADS * ADVECT_PTS);
     const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch, a->keep_pos ? 1 : 0};
-    advect_kernel<WRAP, MODE, OffT><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
-        a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase, g,
-        a->hist_buf[a->cellbuf], a->dense.cell_cap, a->keep_cells ? 1 : 0);
+    if (nf == 1)
+        advect_kernel<WRAP, MODE, OffT><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
+            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase, g,
+            a->hist_buf[a->cellbuf], a->dense.cell_cap, a->keep_cells ? 1 : 0);
+    else
+        advect_fused_kernel<WRAP, MODE, OffT><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
+            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase,
+            a->nframes, nf, g, a->hist, a->hist_stride / sizeof(uint32_t), a->cellbuf, a->hist_ring,
+            a->dense.cell_cap, a->keep_cells ? 1 : 0);
 }
 
 template <bool WRAP, int MODE>
-static void launch_advect_m(clumpy_advect* a, uint32_t phase) {
-    if (a->off16) launch_advect_t<WRAP, MODE, uint16_t>(a, phase);
-    else launch_advect_t<WRAP, MODE, uint32_t>(a, phase);
+static void launch_advect_m(clumpy_advect* a, uint32_t phase, int nf) {
+    if (a->off16) launch_advect_t<WRAP, MODE, uint16_t>(a, phase, nf);
+    else launch_advect_t<WRAP, MODE, uint32_t>(a, phase, nf);
 }
 
 template <bool WRAP>
-static void launch_advect(clumpy_advect* a, uint32_t phase, bool splat) {
-    if (!splat) launch_advect_m<WRAP, CELL_NONE>(a, phase);
-    else if (a->cell_mode == CELL_U8) launch_advect_m<WRAP, CELL_U8>(a, phase);
-    else if (a->cell_mode == CELL_F16) launch_advect_m<WRAP, CELL_F16>(a, phase);
-    else if (a->cell_mode == CELL_X64) launch_advect_m<WRAP, CELL_X64>(a, phase);
-    else launch_advect_m<WRAP, CELL_U32>(a, phase);
+static void launch_advect(clumpy_advect* a, uint32_t phase, bool splat, int nf = 1) {
+    if (!splat) launch_advect_m<WRAP, CELL_NONE>(a, phase, nf);
+    else if (a->cell_mode == CELL_U8) launch_advect_m<WRAP, CELL_U8>(a, phase, nf);
+    else if (a->cell_mode == CELL_F16) launch_advect_m<WRAP, CELL_F16>(a, phase, nf);
+    else if (a->cell_mode == CELL_X64) launch_advect_m<WRAP, CELL_X64>(a, phase, nf);
+    else launch_advect_m<WRAP, CELL_U32>(a, phase, nf);
 }
 
-// ev (optional): 4 events recorded before the advect kernel, after it, after the composite kernel and
-// after the counter clear, for clumpy_cuda_advect_profile.
-static int advect_one_frame(clumpy_advect* a, cudaEvent_t* ev = nullptr) {
+// How many frames the next advect launch may cover: at most `want` and a->fuse, never across a
+// regroup or the warm-up / recording boundary (where, with decay 0, frames start to splat).
+static uint32_t advect_group_size(const clumpy_advect* a, uint32_t want) {
+    uint32_t nf = std::min<uint32_t>(std::max<uint32_t>(want, 1u), (uint32_t)a->fuse);
+    nf = std::min<uint32_t>(nf, a->nframes - a->simframe % a->nframes);
+    if (a->regroup_every) nf = std::min<uint32_t>(nf, a->regroup_every - std::min(a->frames_since_regroup, a->regroup_every - 1u));
+    return std::max<uint32_t>(nf, 1u);
+}
+
+// `nf` simulation frames: ONE advect launch on the main stream (frame f of the group counts into
+// counter image (cellbuf + f) % ring), then per frame a composite and a clear of its counter image on
+// `side` -- the high-priority aux stream when overlapping, so that they share the SMs with the advect
+// launch of the NEXT group (the advect kernel is DRAM-bound, the composite issue-bound), the main
+// stream otherwise and always while profiling.
+// ev (optional, nf = 1): 4 events recorded before the advect kernel, after it, after the composite kernel
+// and after the counter clear, for clumpy_cuda_advect_profile.  kev (optional): 2 events around the
+// advect launch alone, in the pipeline as it runs (clumpy_cuda_advect_profile_fused).
+static int advect_group(clumpy_advect* a, uint32_t nf, cudaEvent_t* ev = nullptr, cudaEvent_t* kev = nullptr) {
     clumpy_cuda_ctx* ctx = a->ctx;
     const uint32_t s = a->simframe;
     const bool warm = s < a->nframes;
     const bool splat = !(warm && a->decay == 0.0f); // advect_points.cc:154
     const uint32_t phase = s % a->nframes;
-    // Frame s counts into image b on the main stream; its composite + clear run on `side`, which is
-    // the high-priority aux stream when overlapping (so they share the SMs with the advect kernel
-    // of frame s+1) and the main stream otherwise (and always while profiling with events).
     const bool overlap = a->overlap && !ev;
     const cudaStream_t main_stream = ctx->stream;
     const cudaStream_t side = overlap ? ctx->aux_stream : main_stream;
-    const int b = a->cellbuf;
-    uint32_t* const cells = a->hist_buf[b];
-    if (splat && a->clear_pending[b]) { // image b was last used two frames ago: wait for its clear
-        CK(cudaStreamWaitEvent(main_stream, a->cleared[b], 0));
-        a->clear_pending[b] = false;
-    }
+    const int ring = a->hist_ring, b0 = a->cellbuf;
+    if (splat)
+        for (uint32_t f = 0; f < nf; ++f) { // these images were last used ring frames ago: wait for their clears
+            const int b = (b0 + (int)f) % ring;
+            if (a->clear_pending[b]) {
+                CK(cudaStreamWaitEvent(main_stream, a->cleared[b], 0));
+                a->clear_pending[b] = false;
+            }
+        }
     if (ev) CK(cudaEventRecord(ev[0], main_stream));
+    if (kev) CK(cudaEventRecord(kev[0], main_stream));
     if (a->npts) {
-        if (a->wrapx) launch_advect<true>(a, phase, splat);
-        else launch_advect<false>(a, phase, splat);
+        if (a->wrapx) launch_advect<true>(a, phase, splat, (int)nf);
+        else launch_advect<false>(a, phase, splat, (int)nf);
         CK_LAUNCH(ctx);
     }
     if (ev) CK(cudaEventRecord(ev[1], main_stream));
+    if (kev) CK(cudaEventRecord(kev[1], main_stream));
     if (splat) {
         if (overlap) {
-            CK(cudaEventRecord(a->advected[b], main_stream));
-            CK(cudaStreamWaitEvent(side, a->advected[b], 0));
+            CK(cudaEventRecord(a->advected[0], main_stream));
+            CK(cudaStreamWaitEvent(side, a->advected[0], 0));
         }
-        // write in place unless a frame copy is still reading the current buffer
-        int dst = a->cur;
-        if (a->copy_pending[a->cur]) {
-            dst = a->cur ^ 1;
-            if (a->copy_pending[dst]) {
-                CK(cudaStreamWaitEvent(side, a->copy_done[dst], 0));
-                a->copy_pending[dst] = false;
+        for (uint32_t f = 0; f < nf; ++f) {
+            const int b = (b0 + (int)f) % ring;
+            uint32_t* const cells = a->hist_buf[b];
+            // write in place unless a frame copy is still reading the current buffer
+            int dst = a->cur;
+            if (a->copy_pending[a->cur]) {
+                dst = a->cur ^ 1;
+                if (a->copy_pending[dst]) {
+                    CK(cudaStreamWaitEvent(side, a->copy_done[dst], 0));
+                    a->copy_pending[dst] = false;
+                }
+            }
+            ctx->stream = side; // the launchers enqueue on ctx->stream
+            int rc;
+            if (a->cell_mode == CELL_U8)
+                rc = launch_composite_dense(ctx, a->geom, a->dense, reinterpret_cast<const uint8_t*>(cells), a->wrapx,
+                                            a->img[a->cur], a->img[dst]);
+            else if (a->cell_mode == CELL_F16)
+                rc = launch_composite_half(ctx, a->geom, a->dense, cells, a->wrapx, a->img[a->cur], a->img[dst]);
+            else if (a->cell_mode == CELL_X64)
+                rc = launch_composite_exact(ctx, a->geom, a->rings, cells, a->wrapx, 1, a->decay, a->img[a->cur], a->img[dst]);
+            else
+                rc = launch_composite(ctx, a->geom, a->rings, cells, a->wrapx, 1, a->decay, a->img[a->cur], a->img[dst]);
+            ctx->stream = main_stream;
+            if (rc) return rc;
+            a->cur = dst;
+            if (ev) CK(cudaEventRecord(ev[2], main_stream));
+            if (a->keep_cells && a->hist_bytes % 16 == 0) {
+                const size_t n16 = a->hist_bytes / 16;
+                const uint32_t grid = (uint32_t)std::min<size_t>((n16 + 255) / 256, (size_t)ctx->sm_count * 8);
+                clear_cells_kernel<<<grid, 256, 0, side>>>(reinterpret_cast<uint4*>(cells), n16);
+                CK_LAUNCH(ctx);
+            } else {
+                CK(cudaMemsetAsync(cells, 0, a->hist_bytes, side));
+            }
+            if (overlap) {
+                CK(cudaEventRecord(a->cleared[b], side));
+                a->clear_pending[b] = true;
+                a->side_dirty = true;
             }
         }
-        ctx->stream = side; // the launchers enqueue on ctx->stream
-        int rc;
-        if (a->cell_mode == CELL_U8)
-            rc = launch_composite_dense(ctx, a->geom, a->dense, reinterpret_cast<const uint8_t*>(cells), a->wrapx,
-                                        a->img[a->cur], a->img[dst]);
-        else if (a->cell_mode == CELL_F16)
-            rc = launch_composite_half(ctx, a->geom, a->dense, cells, a->wrapx, a->img[a->cur], a->img[dst]);
-        else if (a->cell_mode == CELL_X64)
-            rc = launch_composite_exact(ctx, a->geom, a->rings, cells, a->wrapx, 1, a->decay, a->img[a->cur], a->img[dst]);
-        else
-            rc = launch_composite(ctx, a->geom, a->rings, cells, a->wrapx, 1, a->decay, a->img[a->cur], a->img[dst]);
-        ctx->stream = main_stream;
-        if (rc) return rc;
-        a->cur = dst;
-        if (ev) CK(cudaEventRecord(ev[2], main_stream));
-        if (a->keep_cells && a->hist_bytes % 16 == 0) {
-            const size_t n16 = a->hist_bytes / 16;
-            const uint32_t grid = (uint32_t)std::min<size_t>((n16 + 255) / 256, (size_t)ctx->sm_count * 8);
-            clear_cells_kernel<<<grid, 256, 0, side>>>(reinterpret_cast<uint4*>(cells), n16);
-            CK_LAUNCH(ctx);
-        } else {
-            CK(cudaMemsetAsync(cells, 0, a->hist_bytes, side));
-        }
-        if (overlap) {
-            CK(cudaEventRecord(a->cleared[b], side));
-            a->clear_pending[b] = true;
-            a->side_dirty = true;
-            a->cellbuf = b ^ 1;
-        }
+        // One-stream runs have cleared every image again by the time the next launch starts; the ring
+        // only matters (and only advances) when composites lag behind on the side stream or a group
+        // spans several images.
+        if (overlap || nf > 1) a->cellbuf = (b0 + (int)nf) % ring;
     } else if (ev) {
         CK(cudaEventRecord(ev[2], main_stream));
     }
     if (ev) CK(cudaEventRecord(ev[3], main_stream));
-    a->simframe = s + 1;
-    if (a->regroup_every && ++a->frames_since_regroup >= a->regroup_every) return regroup_points(a);
+    a->simframe = s + nf;
+    a->frames_since_regroup += nf;
+    if (a->regroup_every && a->frames_since_regroup >= a->regroup_every) return regroup_points(a);
     return CLUMPY_OK;
 }
 
@@ -1075,9 +1194,11 @@ static int advect_join(clumpy_advect* a) {
 CLUMPY_API int clumpy_cuda_advect_step(clumpy_advect* adv, uint32_t count) {
     REQUIRE(adv, "adv is NULL");
     CK(cudaSetDevice(adv->ctx->device));
-    for (uint32_t i = 0; i < count; ++i) {
-        int rc = advect_one_frame(adv);
+    for (uint32_t i = 0; i < count;) {
+        const uint32_t nf = advect_group_size(adv, count - i);
+        int rc = advect_group(adv, nf);
         if (rc) return rc;
+        i += nf;
     }
     return advect_join(adv);
 }
@@ -1090,7 +1211,7 @@ CLUMPY_API int clumpy_cuda_advect_profile(clumpy_advect* adv, uint32_t count, fl
     int rc = CLUMPY_OK;
     for (auto& e : ev)
         if (cudaEventCreate(&e) != cudaSuccess) { set_error("event creation failed"); rc = CLUMPY_ERR_CUDA; break; }
-    for (uint32_t i = 0; rc == CLUMPY_OK && i < count; ++i) rc = advect_one_frame(adv, &ev[4 * (size_t)i]);
+    for (uint32_t i = 0; rc == CLUMPY_OK && i < count; ++i) rc = advect_group(adv, 1, &ev[4 * (size_t)i]);
     double t[3] = {0, 0, 0};
     if (rc == CLUMPY_OK && cudaStreamSynchronize(adv->ctx->stream) != cudaSuccess) { set_error("profile run failed"); rc = CLUMPY_ERR_CUDA; }
     for (uint32_t i = 0; rc == CLUMPY_OK && i < count; ++i)
@@ -1103,6 +1224,40 @@ CLUMPY_API int clumpy_cuda_advect_profile(clumpy_advect* adv, uint32_t count, fl
     if (advect_ms) *advect_ms = (float)(t[0] / count);
     if (composite_ms) *composite_ms = (float)(t[1] / count);
     if (clear_ms) *clear_ms = (float)(t[2] / count);
+    return rc;
+}
+
+// The advect launch as the pipeline runs it -- several frames per launch, composites of the previous
+// group sharing the GPU -- timed with CUDA events around the launch alone.  Runs `groups` full groups
+// (groups cut short by a regroup or the recording boundary are run but not counted).  Synchronises.
+CLUMPY_API int clumpy_cuda_advect_profile_fused(clumpy_advect* adv, uint32_t groups, float* launch_ms,
+                                                uint32_t* frames_per_launch) {
+    REQUIRE(adv && groups > 0 && launch_ms && frames_per_launch, "bad argument");
+    CK(cudaSetDevice(adv->ctx->device));
+    std::vector<cudaEvent_t> ev(2 * (size_t)groups, nullptr);
+    std::vector<bool> full(groups, false);
+    int rc = CLUMPY_OK;
+    for (auto& e : ev)
+        if (cudaEventCreate(&e) != cudaSuccess) { set_error("event creation failed"); rc = CLUMPY_ERR_CUDA; break; }
+    for (uint32_t g = 0; rc == CLUMPY_OK && g < groups; ++g) {
+        const uint32_t nf = advect_group_size(adv, (uint32_t)adv->fuse);
+        full[g] = nf == (uint32_t)adv->fuse;
+        rc = advect_group(adv, nf, nullptr, &ev[2 * (size_t)g]);
+    }
+    if (rc == CLUMPY_OK) rc = advect_join(adv);
+    if (rc == CLUMPY_OK && cudaStreamSynchronize(adv->ctx->stream) != cudaSuccess) { set_error("profile run failed"); rc = CLUMPY_ERR_CUDA; }
+    double total = 0;
+    uint32_t counted = 0;
+    for (uint32_t g = 0; rc == CLUMPY_OK && g < groups; ++g) {
+        if (!full[g]) continue;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[2 * (size_t)g], ev[2 * (size_t)g + 1]);
+        total += ms;
+        ++counted;
+    }
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    *launch_ms = counted ? (float)(total / counted) : 0.f;
+    *frames_per_launch = (uint32_t)adv->fuse;
     return rc;
 }
 

@@ -165,6 +165,13 @@ int clumpy_cuda_advect_step(clumpy_advect* adv, uint32_t count);
 int clumpy_cuda_advect_profile(clumpy_advect* adv, uint32_t count, float* advect_ms,
                                float* composite_ms, float* clear_ms);
 
+/* clumpy_cuda_advect_step advances up to 4 frames per advect launch (positions stay in registers;
+ * CLUMPY_CUDA_FUSE=1 disables).  This runs `groups` such launches as the pipeline runs them --
+ * composites of the previous group sharing the GPU -- and returns the mean duration of one launch
+ * (CUDA events around the launch alone) and the frames it covers.  Synchronises. */
+int clumpy_cuda_advect_profile_fused(clumpy_advect* adv, uint32_t groups, float* launch_ms,
+                                     uint32_t* frames_per_launch);
+
 /* ---- one simulation frame split at its exchange point (multi-GPU) ------------------------------
  * Points advect independently, so they are sharded across GPUs, each with the whole velocity field.
  * What the shards share is the splat: every GPU counts ITS points into a private counter image (one

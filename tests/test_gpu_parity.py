@@ -429,3 +429,78 @@ def test_cull_points_golden_and_edge_cases(ctx, oracle_mod, golden):
     assert len(ctx.cull_points(inside, -ones)) == 0
     assert np.array_equal(ctx.cull_points(inside, ones), inside)
     assert ctx.cull_points(np.zeros((0, 2), np.float32), ones).shape == (0, 2)
+
+
+# ---- several frames per advect launch (clumpy_cuda_advect_step groups up to 4) --------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells", ["auto", "f16", "u8", "u32", "exact"])
+@pytest.mark.parametrize("k,decay,nframes,overlap", [(3, 0.97, 7, "1"), (1, 0.9, 5, "0"), (5, -0.95, 6, "1"), (3, 0.0, 5, "1")])
+def test_fused_launches_equal_frame_by_frame(ctx, oracle_mod, monkeypatch, cells, k, decay, nframes, overlap):
+    """step(n) in one call (groups of up to 4 frames per launch, ring of counter images, composites on the
+    side stream) must leave exactly the state that n calls of step(1) leave -- which the tests above pin
+    to the oracle -- in every cell mode, across the warm-up / recording boundary (decay 0: splatting starts
+    there), across regroups, in x-wrap mode, and it must agree with the oracle itself."""
+    if cells != "auto":
+        monkeypatch.setenv("CLUMPY_CUDA_CELLS", cells)
+    monkeypatch.setenv("CLUMPY_CUDA_OVERLAP", overlap)
+    monkeypatch.setenv("CLUMPY_CUDA_REGROUP", "3")
+    w, h, n = 192, 128, 30000
+    pot, _, _ = oracle_mod.generate_simplex(w, h, 1.0, 5.0, 4)
+    vel, _, _ = oracle_mod.curl_2d(pot)
+    pts = ((np.random.default_rng(8).random((n, 2)) * 1.06 - 0.03) * [w, h]).astype(np.float32)
+    one = ctx.advect(pts, vel, 45.0, k, decay, nframes)
+    monkeypatch.setenv("CLUMPY_CUDA_FUSE", "4")
+    many = ctx.advect(pts, vel, 45.0, k, decay, nframes)
+    ref = oracle_mod.Advect(pts, vel, 45.0, k, decay, nframes)
+    try:
+        done = 0
+        for chunk in (1, 4, 3, 2, 4):  # 14 = 2 * 7 frames at most; groups 1 | 4 | 3 | 2 | 4
+            chunk = min(chunk, 2 * nframes - done)
+            if chunk == 0:
+                break
+            many.step(chunk)
+            for _ in range(chunk):
+                one.step(1)
+                ref.step()
+            done += chunk
+            assert np.array_equal(many.points().view(np.uint32), one.points().view(np.uint32)), done
+            assert np.array_equal(many.image(), one.image()), done
+            assert np.array_equal(many.points().view(np.uint32), ref.points().view(np.uint32)), done
+            if cells in ("auto", "u32", "exact") or k <= 3:  # (forced table replay with k = 5 is outside its regime)
+                frac, worst = frame_agreement(many.image(), ref.image())
+                assert frac >= 0.999, (done, frac, worst)
+    finally:
+        one.close()
+        many.close()
+        ref.close()
+
+
+@pytest.mark.gpu
+def test_fused_launches_with_frame_copies_in_flight(ctx, oracle_mod, monkeypatch):
+    """The frame read-back ping-pong (frame_async) still sees every frame when the frames in between are
+    advanced by fused launches."""
+    import clumpy_b200
+    monkeypatch.setenv("CLUMPY_CUDA_OVERLAP", "1")
+    w, h, n, nframes = 256, 96, 40000, 6
+    pot, _, _ = oracle_mod.generate_simplex(w, h, 1.0, 6.0, 2)
+    vel, _, _ = oracle_mod.curl_2d(pot)
+    pts = (np.random.default_rng(1).random((n, 2)) * [w, h]).astype(np.float32)
+    adv = ctx.advect(pts, vel, 50.0, 3, 0.96, nframes)
+    ref = oracle_mod.Advect(pts, vel, 50.0, 3, 0.96, nframes)
+    bufs = [np.empty((h, w), np.uint8) for _ in range(4)]
+    want = []
+    try:
+        for i, chunk in enumerate((4, 3, 4, 1)):
+            adv.step(chunk)
+            adv.frame_async(bufs[i])      # the copy is in flight while the next groups run
+            for _ in range(chunk):
+                ref.step()
+            want.append(ref.image())
+        adv.wait_frames()
+        for i in range(4):
+            frac, worst = frame_agreement(bufs[i], want[i])
+            assert frac >= 0.999, (i, frac, worst)
+    finally:
+        adv.close()
+        ref.close()
