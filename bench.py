@@ -51,7 +51,9 @@ ALGO_BYTES_PER_PIXEL_FRAME = 2  # u8 framebuffer read + write
 # round-1 `ncu --set full` capture (profiles/r1_ncu_full_summary.txt: 505.756 MB read + 159.334 MB
 # written).  Not measured by this script: a number taken under a profiler is never a bench value.
 NCU_TRAFFIC_BYTES_ADVECT_KERNEL_C4 = 505_756_000 + 159_334_000
-NCU_TRAFFIC_BYTES_FUSED_KERNEL_C4 = None  # filled in from the ncu capture of the 4-frame kernel (profiles/)
+# the 4-frames-per-launch kernel (profiles/r1_ncu_fused_kernel_summary.txt: 713.551 MB read + 352.322 MB written
+# per launch, i.e. per 4 frames of all 16.7 M points: 57 % of its 1879 MB of algorithmic bytes)
+NCU_TRAFFIC_BYTES_FUSED_KERNEL_C4 = 713_551_360 + 352_322_304
 
 
 def measured_peaks():
