@@ -12,8 +12,8 @@ NVFLAGS  := $(ARCH) -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -Iinclude 
             -Xcompiler -fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function $(EXTRA_NVFLAGS)
 CSRC     := clumpy_b200/csrc
 CUFILES  := $(CSRC)/context.cu $(CSRC)/simplex.cu $(CSRC)/curl.cu $(CSRC)/splat.cu \
-            $(CSRC)/composite_dense.cu $(CSRC)/composite_exact.cu $(CSRC)/advect.cu $(CSRC)/producers.cu
-CUOBJS   := $(CUFILES:.cu=.o)
+            $(CSRC)/composite_group.cu $(CSRC)/composite_exact.cu $(CSRC)/advect.cu $(CSRC)/producers.cu $(CSRC)/microbench.cu
+CUOBJS   := $(CUFILES:.cu=.o) $(CSRC)/age_offsets.o
 LIB      := clumpy_b200/libclumpy_cuda.so
 HOST     := clumpy_b200/host
 CLI      := clumpy_b200/clumpy
@@ -23,8 +23,12 @@ all: lib cli oracle
 
 lib: $(LIB)
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/internal.h $(CSRC)/device_utils.cuh $(CSRC)/rings.cuh include/clumpy_cuda.h
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/internal.h $(CSRC)/device_utils.cuh $(CSRC)/rings.cuh $(CSRC)/advect_kernels.cuh include/clumpy_cuda.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+# plain host code (no CUDA): g++ so that function multi-versioning (AVX2 clone of the generator) is available
+$(CSRC)/%.o: $(CSRC)/%.cc $(CSRC)/internal.h
+	$(CXX) -std=c++17 -O3 -fPIC -fvisibility=hidden -Wall -c $< -o $@
 
 $(LIB): $(CUOBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $^

@@ -38,6 +38,7 @@ SIGNATURES = {
     "clumpy_cuda_timer_start": (C.c_int, [C.c_void_p]),
     "clumpy_cuda_timer_stop": (C.c_int, [C.c_void_p, _f32p]),
     "clumpy_cuda_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "clumpy_cuda_atomic_peak": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int, _f32p]),
     "clumpy_cuda_simplex_perm": (C.c_int, [C.c_int64, _i16p]),
     "clumpy_cuda_generate_simplex": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_double,
                                                C.c_double, C.c_int64, C.c_void_p, _f32p, _f32p]),
@@ -56,9 +57,11 @@ SIGNATURES = {
     "clumpy_cuda_advect_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                            C.c_uint32, C.c_uint32, C.c_float, C.c_int, C.c_float,
                                            C.c_int, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "clumpy_cuda_advect_begin_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "clumpy_cuda_row_histogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, _u32p]),
     "clumpy_cuda_advect_step": (C.c_int, [C.c_void_p, C.c_uint32]),
-    "clumpy_cuda_advect_profile": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _f32p, _f32p]),
-    "clumpy_cuda_advect_profile_fused": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _u32p]),
+    "clumpy_cuda_advect_record": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "clumpy_cuda_advect_profile_stages": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, _f32p, _f32p, _u32p]),
     "clumpy_cuda_advect_count": (C.c_int, [C.c_void_p]),
     "clumpy_cuda_advect_cells": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                            _u32p, _u32p, _u32p, _u32p]),
@@ -71,18 +74,19 @@ SIGNATURES = {
     "clumpy_cuda_advect_route_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint32,
                                                  C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "clumpy_cuda_advect_route_peers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
-    "clumpy_cuda_advect_route": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
-    "clumpy_cuda_advect_drain": (C.c_int, [C.c_void_p, C.c_void_p]),
     "clumpy_cuda_advect_owned_rows": (C.c_int, [C.c_void_p, _u32p, _u32p]),
     "clumpy_cuda_advect_route_steps": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "clumpy_cuda_advect_route_record": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
     "clumpy_cuda_advect_route_errors": (C.c_int, [C.c_void_p, _u32p]),
     "clumpy_cuda_pendulum_phase": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "clumpy_cuda_pendulum_phase_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float,
                                                  C.c_float, C.c_float, C.c_void_p]),
     "clumpy_cuda_cull_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
                                           C.c_void_p, _u32p]),
-    "clumpy_cuda_advect_route_profile": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _f32p, _f32p]),
+    "clumpy_cuda_advect_route_profile": (C.c_int, [C.c_void_p, C.c_uint32, _f32p, _f32p, _f32p, _u32p]),
     "clumpy_cuda_advect_simframe": (C.c_int, [C.c_void_p, _u32p]),
+    "clumpy_cuda_advect_npts": (C.c_int, [C.c_void_p, _u32p]),
+    "clumpy_cuda_advect_read_points_indexed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "clumpy_cuda_advect_frame_async": (C.c_int, [C.c_void_p, C.c_void_p]),
     "clumpy_cuda_advect_wait_frames": (C.c_int, [C.c_void_p]),
     "clumpy_cuda_advect_read_points": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -92,6 +96,20 @@ SIGNATURES = {
                                             C.c_uint32, C.c_uint32, C.c_float, C.c_int, C.c_float,
                                             C.c_int, C.c_uint32, C.c_void_p, FRAME_FN, C.c_void_p]),
 }
+
+CELLS_AUTO, CELLS_COUNT, CELLS_F16, CELLS_U32, CELLS_EXACT = 0, 1, 2, 3, 4
+_CELLS = {"auto": CELLS_AUTO, "count": CELLS_COUNT, "f16": CELLS_F16, "u32": CELLS_U32, "exact": CELLS_EXACT}
+
+
+class AdvectDesc(C.Structure):
+    """struct clumpy_advect_desc (include/clumpy_cuda.h)."""
+    _fields_ = [("size", C.c_uint32), ("pts", C.c_void_p), ("npts", C.c_uint32), ("pts_on_device", C.c_int),
+                ("vel", C.c_void_p), ("vel_on_device", C.c_int), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("step_size", C.c_float), ("kernel_size", C.c_int), ("decay", C.c_float), ("wrapx", C.c_int),
+                ("nframes", C.c_uint32), ("age_offset", C.c_void_p), ("age_on_device", C.c_int),
+                ("shard_row_lo", C.c_uint32), ("shard_row_hi", C.c_uint32), ("cells", C.c_int), ("overlap", C.c_int),
+                ("fuse", C.c_int), ("regroup", C.c_int), ("cell_rows_multiple", C.c_int)]
+
 
 _LIB = None
 
@@ -204,6 +222,13 @@ class Context:
         _check(lib().clumpy_cuda_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def atomic_peak(self, op, pattern, region_bytes, nupdates, hot_cells=1, iters=5):
+        """Mean ms of one launch of `nupdates` reductions (op 0: f16x2, 1: u32; pattern 0: uniform, 1: hot
+        spot, 2: local) -- the atomic leg of the splat roofline (tools/atomic_peak.py)."""
+        ms = C.c_float()
+        _check(lib().clumpy_cuda_atomic_peak(self._h, op, pattern, region_bytes, nupdates, hot_cells, iters, C.byref(ms)))
+        return ms.value
+
     # ---- commands, host buffers in and out ------------------------------------------------------
 
     def generate_simplex(self, width, height, amplitude, frequency, seed, out=None):
@@ -281,8 +306,21 @@ class Context:
             C.byref(lo) if want_range else None, C.byref(hi) if want_range else None))
         return (lo.value, hi.value) if want_range else None
 
-    def advect(self, pts, vel, step_size, kernel_size, decay, nframes, age_offset=None):
-        return Advect(self, pts, vel, step_size, kernel_size, decay, nframes, age_offset)
+    def advect(self, pts, vel, step_size, kernel_size, decay, nframes, age_offset=None, **options):
+        """options: the fields of clumpy_advect_desc beyond the command's arguments -- cells ("auto" | "count" |
+        "f16" | "u32" | "exact"), overlap, fuse, regroup, cell_rows_multiple, shard_rows=(lo, hi), and
+        width / height when pts / vel / age_offset are raw device addresses (integers)."""
+        return Advect(self, pts, vel, step_size, kernel_size, decay, nframes, age_offset, **options)
+
+    def row_histogram(self, pts, height, npts=None):
+        """Points per home row (numpy uint32, `height` entries); pts: (N, 2) array or a device address + npts."""
+        on_device = isinstance(pts, (int, np.integer))
+        if not on_device:
+            pts = _f32(pts)
+            npts = len(pts)
+        rows = np.empty(height, np.uint32)
+        _check(lib().clumpy_cuda_row_histogram(self._h, _vp(pts), npts, int(on_device), height, rows.ctypes.data_as(_u32p)))
+        return rows
 
     def advect_points(self, pts, vel, step_size, kernel_size, decay, nframes, on_frame=None):
         """The whole `clumpy advect_points` command; returns (nframes, H, W) u8 unless on_frame
@@ -308,40 +346,68 @@ class Context:
 
 class Advect:
     """Device-resident advect_points run (advect_points.cc:64-183).  A negative `decay` selects the
-    reference's x-wrap mode, as the command does (:78-81)."""
+    reference's x-wrap mode, as the command does (:78-81).  pts / vel / age_offset may be numpy arrays (host)
+    or integers (device addresses; then npts= / width= / height= say how big they are)."""
 
-    def __init__(self, ctx, pts, vel, step_size, kernel_size, decay, nframes, age_offset=None):
+    def __init__(self, ctx, pts, vel, step_size, kernel_size, decay, nframes, age_offset=None, *, npts=None,
+                 width=None, height=None, cells="auto", overlap=0, fuse=0, regroup=0, cell_rows_multiple=0,
+                 shard_rows=None):
         self.ctx = ctx
-        pts, vel = _f32(pts), _f32(vel)
-        if pts.ndim != 2 or pts.shape[1] != 2:
-            raise ValueError("Input points have wrong shape.")
-        if vel.ndim != 3 or vel.shape[2] != 2:
-            raise ValueError("Velocities have wrong shape.")
-        self.h, self.w = vel.shape[:2]
-        self.n = len(pts)
-        self.nframes = nframes
-        wrapx, decay = (1, -decay) if decay < 0 else (0, decay)
-        if age_offset is not None:
+        d = AdvectDesc()
+        d.size = C.sizeof(AdvectDesc)
+        self._keep = []
+        if isinstance(pts, (int, np.integer)):
+            d.pts, d.npts, d.pts_on_device = int(pts), int(npts), 1
+        else:
+            pts = _f32(pts)
+            if pts.ndim != 2 or pts.shape[1] != 2:
+                raise ValueError("Input points have wrong shape.")
+            d.pts, d.npts, d.pts_on_device = pts.ctypes.data, len(pts), 0
+            self._keep.append(pts)
+        if isinstance(vel, (int, np.integer)):
+            d.vel, d.vel_on_device, self.w, self.h = int(vel), 1, int(width), int(height)
+        else:
+            vel = _f32(vel)
+            if vel.ndim != 3 or vel.shape[2] != 2:
+                raise ValueError("Velocities have wrong shape.")
+            d.vel, d.vel_on_device = vel.ctypes.data, 0
+            self.h, self.w = vel.shape[:2]
+            self._keep.append(vel)
+        if age_offset is None:
+            d.age_offset = None
+        elif isinstance(age_offset, (int, np.integer)):
+            d.age_offset, d.age_on_device = int(age_offset), 1
+        else:
             age_offset = np.ascontiguousarray(age_offset, np.uint32)
+            d.age_offset, d.age_on_device = age_offset.ctypes.data, 0
+            self._keep.append(age_offset)
+        d.width, d.height = self.w, self.h
+        wrapx, decay = (1, -decay) if decay < 0 else (0, decay)
+        d.step_size, d.kernel_size, d.decay, d.wrapx, d.nframes = step_size, kernel_size, decay, wrapx, nframes
+        if shard_rows is not None:
+            d.shard_row_lo, d.shard_row_hi = int(shard_rows[0]), int(shard_rows[1])
+        d.cells, d.overlap, d.fuse, d.regroup, d.cell_rows_multiple = _CELLS[cells], overlap, fuse, regroup, cell_rows_multiple
+        self.nframes = nframes
         self._h = C.c_void_p()
-        _check(lib().clumpy_cuda_advect_begin(ctx._h, _vp(pts), self.n, _vp(vel), self.w, self.h,
-                                              step_size, kernel_size, decay, wrapx, nframes,
-                                              _vp(age_offset), C.byref(self._h)))
+        _check(lib().clumpy_cuda_advect_begin_ex(ctx._h, C.byref(d), C.byref(self._h)))
+        self._keep = []  # the library has synchronised: the inputs are on the device
+        n = C.c_uint32()
+        _check(lib().clumpy_cuda_advect_npts(self._h, C.byref(n)))
+        self.n = n.value
 
     def step(self, count=1):
         _check(lib().clumpy_cuda_advect_step(self._h, count))
 
-    def profile(self, count):
-        """-> mean ms per frame of (advect+count kernel, composite kernel, counter clear)."""
-        a, c, z = C.c_float(), C.c_float(), C.c_float()
-        _check(lib().clumpy_cuda_advect_profile(self._h, count, C.byref(a), C.byref(c), C.byref(z)))
-        return a.value, c.value, z.value
+    def record(self, count, dst, frame_stride=None):
+        """step(count), every frame copied to dst (pinned host memory: array or address) + i * frame_stride."""
+        _check(lib().clumpy_cuda_advect_record(self._h, count, _vp(dst), frame_stride or self.w * self.h))
 
-    def profile_fused(self, groups):
-        """-> (mean ms of one advect launch inside the running pipeline, frames per launch)."""
-        ms, nf = C.c_float(), C.c_uint32()
-        _check(lib().clumpy_cuda_advect_profile_fused(self._h, groups, C.byref(ms), C.byref(nf)))
-        return ms.value, nf.value
+    def profile_stages(self, groups, serial=False):
+        """-> (mean ms of one advect launch, mean ms of one group's composite work, frames per launch);
+        serial: each kernel alone on the GPU instead of as the pipeline overlaps them."""
+        a, c, nf = C.c_float(), C.c_float(), C.c_uint32()
+        _check(lib().clumpy_cuda_advect_profile_stages(self._h, groups, int(serial), C.byref(a), C.byref(c), C.byref(nf)))
+        return a.value, c.value, nf.value
 
     @property
     def simframe(self):
@@ -381,22 +447,18 @@ class Advect:
         arr = (C.c_void_p * len(inbox_ptrs))(*[C.c_void_p(int(p) if p else 0) for p in inbox_ptrs])
         _check(lib().clumpy_cuda_advect_route_peers(self._h, arr))
 
-    def route(self):
-        """Advect + route this frame; -> device address of the world per-destination counts."""
-        p = C.c_void_p()
-        _check(lib().clumpy_cuda_advect_route(self._h, C.byref(p)))
-        return p.value
-
-    def drain(self, counts_all_dev):
-        _check(lib().clumpy_cuda_advect_drain(self._h, _vp(counts_all_dev)))
-
     def route_steps(self, count):
         _check(lib().clumpy_cuda_advect_route_steps(self._h, count))
 
-    def route_profile(self, count):
-        a, b, c = C.c_float(), C.c_float(), C.c_float()
-        _check(lib().clumpy_cuda_advect_route_profile(self._h, count, C.byref(a), C.byref(b), C.byref(c)))
-        return a.value, b.value, c.value
+    def route_record(self, count, dst, frame_stride):
+        """route_steps(count), this rank's rows of every frame copied to dst + i * frame_stride (pinned)."""
+        _check(lib().clumpy_cuda_advect_route_record(self._h, count, _vp(dst), frame_stride))
+
+    def route_profile(self, groups):
+        """-> (route, drain incl. wait, band composite) mean ms per GROUP, frames per group."""
+        a, b, c, nf = C.c_float(), C.c_float(), C.c_float(), C.c_uint32()
+        _check(lib().clumpy_cuda_advect_route_profile(self._h, groups, C.byref(a), C.byref(b), C.byref(c), C.byref(nf)))
+        return a.value, b.value, c.value, nf.value
 
     def route_errors(self):
         n = C.c_uint32()
@@ -423,6 +485,12 @@ class Advect:
         out = np.empty((self.n, 2), np.float32)
         _check(lib().clumpy_cuda_advect_read_points(self._h, _vp(out)))
         return out
+
+    def points_indexed(self):
+        """Shards: (positions in storage order, index of each in the caller's list)."""
+        pos, idx = np.empty((self.n, 2), np.float32), np.empty(self.n, np.uint32)
+        _check(lib().clumpy_cuda_advect_read_points_indexed(self._h, _vp(pos), _vp(idx)))
+        return pos, idx
 
     def image(self):
         out = np.empty((self.h, self.w), np.uint8)

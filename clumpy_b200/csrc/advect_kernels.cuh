@@ -1,0 +1,601 @@
+// advect_kernels.cuh -- device side of clumpy `advect_points` for sm_100a (host side: advect.cu).
+//
+// Replaces the per-point loop of commands/advect_points.cc:144-153,163-171 and the hit loop of
+// splat_points.cc:142-160.  Facts the kernels rely on:
+//   * velocity lookup is NEAREST texel (advect_points.cc:27-36), index conversion via int64;
+//   * pt += step * v is a rounded multiply then a rounded add (the reference binary has no FMA);
+//   * the age / age_offset bookkeeping (:124-135,147-152,166-170) is equivalent to
+//         "point i returns to its original position at the end of simulation frame s
+//          iff s % nframes == age_offset_i",
+//     so no per-point age is stored;
+//   * trajectories never depend on the framebuffer.
+#pragma once
+
+#include "device_utils.cuh"
+#include "internal.h"
+
+namespace clumpy {
+
+constexpr int ADVECT_THREADS = 256;
+constexpr int ADVECT_PTS = 4;      // points per thread (independent load chains in flight)
+constexpr int ADVECT_MAX_FUSE = 8; // simulation frames one launch can advance (= GC_MAX_FRAMES)
+
+// How a point is counted into the splat accumulator.
+enum CellMode : int {
+    CELL_NONE = -1, // frame without a splat (warm-up with decay == 0)
+    CELL_U32 = 0,   // 32-bit counters, one RED.ADD per point (any sprite)
+    CELL_F16 = 2,   // half-float counters, two per word, one RED.ADD.F16x2 per point: a half counts
+                    // exactly to 2048 and then stays put, so it saturates by itself and cannot carry
+    CELL_X64 = 3,   // 64-bit cells = count (24 bits) + sum of original point indices (40 bits), one
+                    // 64-bit RED.ADD per point: keeps the reference's hit order (composite_exact.cu)
+};
+
+__device__ __forceinline__ void cell_add_f16(uint32_t* __restrict__ words, long long cell) {
+    // (1, 0) or (0, 1) as a half2 bit pattern: 0x3C00 is 1.0
+    const uint32_t one = (cell & 1) ? 0x3C000000u : 0x00003C00u;
+    asm volatile("red.global.add.noftz.f16x2 [%0], %1;" :: "l"(words + (cell >> 1)), "r"(one) : "memory");
+}
+
+// Counts a point whose truncated position is (cx, cy) (splat_points.cc:143-144) into `hist`.
+// Half cells in x-wrap mode: the group composite (composite_group.cu) reads its halo columns as they are, so a
+// point within `halo` columns of the left / right edge is also counted into the halo column on the other
+// side -- the cell its wrapped taps would be read from (splat_points.cc:149-151).
+template <bool WRAP, int MODE>
+__device__ __forceinline__ void count_point(uint32_t* __restrict__ hist, int32_t cx, int32_t cy, const GeomDev& g,
+                                            uint32_t slot) {
+    const long long at = hist_index<WRAP>(cx, cy, g);
+    if (at < 0) return;
+    if (MODE == CELL_X64) {
+        // exact-order path: the points are in the caller's order, so the slot IS the original index
+        atomicAdd(reinterpret_cast<unsigned long long*>(hist) + at, ((unsigned long long)slot << 24) | 1ull);
+    } else if (MODE == CELL_U32) {
+        atomicAdd(hist + at, 1u);
+    } else if (MODE == CELL_F16) {
+        cell_add_f16(hist, at);
+        if (WRAP && g.halo > 0) {
+            int32_t m = cx % g.width;
+            if (m < 0) m += g.width;
+            if (m >= g.width - g.halo) cell_add_f16(hist, at - g.width);
+            if (m < g.halo) cell_add_f16(hist, at + g.width);
+        }
+    }
+}
+
+// Up to ADVECT_MAX_FUSE simulation frames per launch ("temporal blocking"): the positions are loaded once,
+// advanced through `nf` frames in registers -- gather, Euler step, reset, count, each frame counting into
+// its own counter image -- and stored once.  Position and phase traffic (20 of the 28 algorithmic bytes per
+// point-step) is paid once per group instead of once per frame; the gathers and the counter updates are what
+// is left per frame.
+//
+// A CTA owns ADVECT_THREADS * ADVECT_PTS consecutive points; thread t takes t, t + 256, t + 512, ... so every
+// warp-wide access covers 32 CONSECUTIVE points: position / offset traffic is perfectly coalesced and, the
+// points being stored in tile order, a warp's gather touches only a few lines.
+struct HistRing {
+    uint32_t* image[ADVECT_MAX_FUSE]; // counter image of frame f of the group
+};
+
+template <bool WRAP, int MODE, typename OffT>
+__global__ void __launch_bounds__(ADVECT_THREADS)
+advect_fused_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
+                    const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
+                    uint32_t width, uint32_t height, float step, uint32_t phase0, uint32_t nframes, int nf,
+                    GeomDev g, HistRing ring) {
+    const uint32_t base = blockIdx.x * (ADVECT_THREADS * ADVECT_PTS) + threadIdx.x;
+    const uint64_t pol = g.keep_pos == 0 ? make_stream_policy() : make_normal_policy();
+    float2 p[ADVECT_PTS];
+    uint32_t off[ADVECT_PTS];
+    bool live[ADVECT_PTS];
+#pragma unroll
+    for (int k = 0; k < ADVECT_PTS; ++k) {
+        const uint32_t i = base + k * ADVECT_THREADS;
+        live[k] = i < npts;
+        p[k] = make_float2(0.f, 0.f);
+        off[k] = 0xFFFFFFFFu;
+        if (live[k]) {
+            p[k] = ld_stream_f2(pos + i, pol);
+            off[k] = ld_stream_off(offset + i, pol);
+        }
+    }
+    uint32_t phase = phase0;
+    for (int f = 0; f < nf; ++f) {
+        float2 v[ADVECT_PTS];
+#pragma unroll
+        for (int k = 0; k < ADVECT_PTS; ++k) { // nearest-texel fetch (advect_points.cc:23-37)
+            uint32_t x = f2u32_x86(p[k].x);
+            const uint32_t y = f2u32_x86(p[k].y);
+            if (WRAP) x = (width + (x % width)) % width;
+            v[k] = make_float2(0.f, 0.f);
+            if (live[k] && x < width && y < height) v[k] = __ldg(vel + ((size_t)y * width + x));
+        }
+#pragma unroll
+        for (int k = 0; k < ADVECT_PTS; ++k) {
+            // pt += step * v: rounded multiply, then rounded add (:146); reset AFTER the move (:147-152,166-170)
+            p[k] = make_float2(__fadd_rn(p[k].x, __fmul_rn(step, v[k].x)), __fadd_rn(p[k].y, __fmul_rn(step, v[k].y)));
+            if (off[k] == phase) p[k] = orig[base + k * ADVECT_THREADS];
+        }
+        phase = phase + 1u == nframes ? 0u : phase + 1u;
+        if (MODE != CELL_NONE) {
+            uint32_t* hist = ring.image[f];
+#pragma unroll
+            for (int k = 0; k < ADVECT_PTS; ++k) // splat_points.cc:143-144: centre texel by (int32_t) truncation
+                if (live[k]) count_point<WRAP, MODE>(hist, f2i32_x86(p[k].x), f2i32_x86(p[k].y), g, base + k * ADVECT_THREADS);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ADVECT_PTS; ++k)
+        if (live[k]) st_stream_f2(pos + base + k * ADVECT_THREADS, p[k], pol);
+}
+
+// ---- multi-GPU: the splat exchange fused into the advect kernel ------------------------------------
+//
+// With G GPUs the counter image is distributed by bands of `chunk` padded rows (band d on GPU d) and
+// never exists as a whole.  Each GPU advects ITS points and, instead of counting them locally and
+// summing dense images afterwards (67 MB per frame at 8192x4096), counts the points that land in its
+// own band straight into its band buffer and writes every other point's cell -- one 4-byte index into
+// the OWNER's band buffer -- into the owner's inbox through peer-mapped memory (NVLink / NVSwitch
+// stores issued from inside the kernel).  A point whose row lies within `halo` rows of a band edge is
+// also sent to the neighbouring band, whose composite needs it, so no separate halo exchange is left.
+//
+// No global slot counters: CTA c of source rank s owns the fixed region [c * ROUTE_BLOCK,
+// (c + 1) * ROUTE_BLOCK) of segment s in every destination's inbox for every frame of the group (a CTA
+// advects ROUTE_BLOCK points and a point sends at most one entry per destination and frame), ranks its
+// entries with a shared-memory atomic, and at the END of the launch leaves the numbers it wrote in the
+// destination's count words [frame][s][c].
+//
+// One launch advances the points by a GROUP of up to ROUTE_MAX_FUSE frames; positions stay in registers.
+// Inside the frame loop there is no barrier and no fence.  The fence is per GROUP: a CTA that is done
+// fences its remote stores at system scope and takes a ticket; the CTA that takes the last ticket stores
+// the group's EPOCH into a flag per source in every peer's memory.  The receiver (drain_group_kernel) waits
+// for every source's epoch, counts the entries into its band buffers and zeroes the count words it used.
+constexpr int ROUTE_MAX_WORLD = 8;
+constexpr uint32_t ROUTE_BLOCK = ADVECT_THREADS * ADVECT_PTS; // points per CTA
+constexpr uint32_t ROUTE_REGION = ROUTE_BLOCK;                // entry slots per (CTA, destination, frame)
+constexpr int ROUTE_MAX_FUSE = ADVECT_MAX_FUSE;               // frames per launch
+constexpr int ROUTE_PARITIES = 4; // inbox slot sets in flight (see route_launch for why 4 is enough)
+constexpr int ROUTE_SETS = 3;     // band-buffer sets: counted into | composited | being zeroed
+
+struct RouteDev {
+    int me, world;
+    int chunk, halo, pitch;             // band geometry in padded rows / cells
+    uint32_t nregion;                   // regions (= CTAs of the largest shard) per source segment
+    uint32_t nframes, phase0;           // reset period; phase of the first frame of the group
+    int nf;                             // frames in this launch
+    size_t inbox_off;                   // uint32 offset of this group's parity inside every inbox
+    size_t inbox_frame_stride;          // ... between consecutive frames of the group
+    size_t cnt_off, cnt_frame_stride;   // the same for the count words
+    uint32_t* inbox[ROUTE_MAX_WORLD];   // rank r's entries (peer-mapped): [parity][frame][source][region][ROUTE_REGION]
+    uint32_t* cnt[ROUTE_MAX_WORLD];     // rank r's count words (peer-mapped): [parity][frame][source][region]
+    uint32_t* flags[ROUTE_MAX_WORLD];   // rank r's epoch flags (peer-mapped): [source]
+    uint32_t* band[ROUTE_MAX_FUSE];     // this rank's band buffer of frame f
+    int band_f16;                       // band cells are half floats (else uint32)
+    int loopback;                       // profiling aid: every "peer" is this rank itself (see route_begin)
+    uint32_t epoch;                     // epoch of the group
+    uint32_t* ticket;                   // CTAs of this launch that are done
+};
+
+// One count into a band buffer.  Half cells in x-wrap mode (wrap_w = image width, else 0): the group
+// composite reads its halo columns as they are, so a cell within `halo` columns of the left / right edge is
+// also counted into the halo column on the other side (see count_point).
+__device__ __forceinline__ void band_add(uint32_t* __restrict__ band, uint32_t entry, int f16, int wrap_w, int halo, int pitch) {
+    if (!f16) { atomicAdd(band + entry, 1u); return; }
+    cell_add_f16(band, (long long)entry);
+    if (wrap_w && halo > 0) {
+        const int m = (int)(entry % (uint32_t)pitch) - halo;
+        if (m >= wrap_w - halo) cell_add_f16(band, (long long)entry - wrap_w);
+        if (m < halo) cell_add_f16(band, (long long)entry + wrap_w);
+    }
+}
+
+// One entry for rank `dst`: the CTA-wide rank comes from a shared-memory atomic, the slot is fixed by
+// the CTA's region, the store goes over NVLink.
+__device__ __forceinline__ void route_send(const RouteDev& rt, int f, uint32_t* cta_n, int dst, uint32_t entry) {
+    const uint32_t r = atomicAdd(cta_n + dst, 1u);
+    rt.inbox[dst][rt.inbox_off + (size_t)f * rt.inbox_frame_stride + ((size_t)rt.me * rt.nregion + blockIdx.x) * ROUTE_REGION + r] = entry;
+}
+
+// A cell of padded row `r` (relative to band `owner`'s first row) and padded column `ux`: counted
+// straight into this rank's band buffer when it is ours, sent to the owner's inbox otherwise; rows
+// within the sprite's reach of a band edge also go to the neighbouring band, whose composite needs them.
+__device__ __forceinline__ void route_cell(const RouteDev& rt, int f, uint32_t* cta_n, int owner, int r, uint32_t ux, int wrap_w) {
+    const uint32_t entry = (uint32_t)((r + rt.halo) * rt.pitch) + ux; // band rows: [halo above | chunk | halo below]
+    if (owner == rt.me) band_add(rt.band[f], entry, rt.band_f16, wrap_w, rt.halo, rt.pitch);
+    else route_send(rt, f, cta_n, owner, entry);
+    if (r < rt.halo && owner > 0) {
+        const uint32_t e = (uint32_t)((r + rt.chunk + rt.halo) * rt.pitch) + ux;
+        if (owner - 1 == rt.me) band_add(rt.band[f], e, rt.band_f16, wrap_w, rt.halo, rt.pitch);
+        else route_send(rt, f, cta_n, owner - 1, e);
+    }
+    if (r >= rt.chunk - rt.halo && owner < rt.world - 1) {
+        const uint32_t e = (uint32_t)((r - rt.chunk + rt.halo) * rt.pitch) + ux;
+        if (owner + 1 == rt.me) band_add(rt.band[f], e, rt.band_f16, wrap_w, rt.halo, rt.pitch);
+        else route_send(rt, f, cta_n, owner + 1, e);
+    }
+}
+
+// The group fence, sender side.  Called by every CTA after a barrier that follows its last remote store:
+// thread 0's fence.sys is cumulative over the stores of the whole CTA (they happen-before it through the
+// barrier); the ticket orders the CTAs; the last one fences again and publishes.
+__device__ __forceinline__ void route_group_fence(const RouteDev& rt) {
+    if (threadIdx.x != 0) return;
+    __threadfence_system();
+    const uint32_t done = atomicAdd(rt.ticket, 1u);
+    if (done != gridDim.x - 1u) return;
+    *rt.ticket = 0u; // for the next launch (launches of one rank are stream-ordered)
+    __threadfence_system();
+    for (int d = 0; d < rt.world; ++d) {
+        const int slot = rt.loopback ? d : rt.me; // loopback: play every source of my own inbox
+        *reinterpret_cast<volatile uint32_t*>(rt.flags[d] + slot) = rt.epoch;
+    }
+}
+
+template <bool WRAP, bool SPLAT, typename OffT, int MINB>
+__global__ void __launch_bounds__(ADVECT_THREADS, MINB)
+advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
+                    const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
+                    uint32_t width, uint32_t height, float step, GeomDev g, RouteDev rt) {
+    __shared__ uint32_t cta_n[ROUTE_MAX_FUSE][ROUTE_MAX_WORLD];
+    if (SPLAT) {
+        if (threadIdx.x < ROUTE_MAX_FUSE * ROUTE_MAX_WORLD) (&cta_n[0][0])[threadIdx.x] = 0u;
+        __syncthreads(); // here, where every warp arrives at once, not after the loads
+    }
+    const uint64_t pol = g.keep_pos == 0 ? make_stream_policy() : make_normal_policy();
+    const uint32_t base = blockIdx.x * ROUTE_BLOCK + threadIdx.x;
+    const int my_lo = rt.me * rt.chunk; // first padded row of this rank's band
+    // positions and reset phases: loaded once for the whole group of frames
+    float2 p[ADVECT_PTS];
+    uint32_t off[ADVECT_PTS];
+    bool live[ADVECT_PTS];
+#pragma unroll
+    for (int k = 0; k < ADVECT_PTS; ++k) {
+        const uint32_t i = base + k * ADVECT_THREADS;
+        live[k] = i < npts;
+        p[k] = make_float2(0.f, 0.f);
+        off[k] = 0xFFFFFFFFu;
+        if (live[k]) {
+            p[k] = ld_stream_f2(pos + i, pol);
+            off[k] = ld_stream_off(offset + i, pol);
+        }
+    }
+    uint32_t phase = rt.phase0;
+    for (int f = 0; f < rt.nf; ++f) {
+        float2 v[ADVECT_PTS];
+#pragma unroll
+        for (int k = 0; k < ADVECT_PTS; ++k) { // nearest-texel fetch (advect_points.cc:23-37)
+            uint32_t x = f2u32_x86(p[k].x);
+            const uint32_t y = f2u32_x86(p[k].y);
+            if (WRAP) x = (width + (x % width)) % width;
+            v[k] = make_float2(0.f, 0.f);
+            if (live[k] && x < width && y < height) v[k] = __ldg(vel + ((size_t)y * width + x));
+        }
+#pragma unroll
+        for (int k = 0; k < ADVECT_PTS; ++k) {
+            // pt += step * v: rounded multiply, then rounded add (:146)
+            p[k] = make_float2(__fadd_rn(p[k].x, __fmul_rn(step, v[k].x)), __fadd_rn(p[k].y, __fmul_rn(step, v[k].y)));
+            if (off[k] == phase) p[k] = orig[base + k * ADVECT_THREADS]; // reset AFTER the move (:147-152,166-170)
+        }
+        phase = phase + 1u == rt.nframes ? 0u : phase + 1u;
+#pragma unroll
+        for (int k = 0; SPLAT && k < ADVECT_PTS; ++k) {
+            // splat_points.cc:143-144: centre texel by (int32_t) truncation; same tests as hist_index
+            const int32_t cx = f2i32_x86(p[k].x), cy = f2i32_x86(p[k].y);
+            const uint32_t uy = (uint32_t)cy + (uint32_t)g.halo;
+            if (!live[k] || uy >= (uint32_t)(g.height + 2 * g.halo)) continue;
+            uint32_t ux;
+            if (WRAP) {
+                int32_t m = cx % g.width;
+                if (m < 0) m += g.width;
+                ux = (uint32_t)(m + g.halo);
+            } else {
+                ux = (uint32_t)cx + (uint32_t)g.halo;
+                if (ux >= (uint32_t)(g.width + 2 * g.halo)) continue;
+            }
+            int r = (int)uy - my_lo, owner = rt.me;
+            if ((uint32_t)r >= (uint32_t)rt.chunk) {
+                owner = min((int)(uy / (uint32_t)rt.chunk), rt.world - 1);
+                r = (int)uy - owner * rt.chunk;
+            }
+            route_cell(rt, f, cta_n[f], owner, r, ux, WRAP ? g.width : 0);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ADVECT_PTS; ++k)
+        if (live[k]) st_stream_f2(pos + base + k * ADVECT_THREADS, p[k], pol);
+    if (!SPLAT) return;
+    __syncthreads(); // every entry of this CTA is written, cta_n is final
+    // the non-zero counts go to their destinations (the receivers zero them again)
+    if (threadIdx.x < (uint32_t)(rt.nf * ROUTE_MAX_WORLD)) {
+        const int f = threadIdx.x / ROUTE_MAX_WORLD, d = threadIdx.x % ROUTE_MAX_WORLD;
+        const uint32_t n = d < rt.world ? cta_n[f][d] : 0u;
+        if (n) *reinterpret_cast<volatile uint32_t*>(rt.cnt[d] + rt.cnt_off + (size_t)f * rt.cnt_frame_stride + (size_t)rt.me * rt.nregion + blockIdx.x) = n;
+    }
+    __syncthreads();
+    route_group_fence(rt);
+}
+
+// The same fence for a rank that has no points this run (no route kernel to carry it).
+__global__ void route_signal_kernel(RouteDev rt) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        __threadfence_system();
+        for (int d = 0; d < rt.world; ++d) *reinterpret_cast<volatile uint32_t*>(rt.flags[d] + (rt.loopback ? d : rt.me)) = rt.epoch;
+    }
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// The receiving half of a group: waits until every source has published the group's epoch (bounded: on a
+// time-out it records the error and does nothing else -- the host turns a non-zero error count into a failed
+// call), then counts the entries of every frame of the group into that frame's band buffer: one warp per
+// (frame, source, region).  Count words are zeroed as they are used: senders only ever write non-zero ones.
+struct DrainDev {
+    const uint32_t* inbox;      // this group's parity: [frame][source][region][ROUTE_REGION]
+    uint32_t* cnt;              // [frame][source][region]
+    size_t inbox_frame_stride, cnt_frame_stride;
+    uint32_t nregion;
+    int world, nf;
+    const uint32_t* flags;      // [source]; NULL: do not wait
+    uint32_t epoch;
+    uint32_t* errors;
+    unsigned long long timeout_ns;
+    uint32_t* band[ROUTE_MAX_FUSE];
+    uint32_t band_cells;
+    int wrap_w, halo, pitch;    // x-wrap mode: image width (else 0); band geometry
+};
+
+template <int CELLS>
+__global__ void __launch_bounds__(256)
+drain_group_kernel(DrainDev d) {
+    if (d.flags) {
+        __shared__ int arrived;
+        if (threadIdx.x == 0) {
+            const unsigned long long t0 = globaltimer_ns();
+            int ok = 1;
+            for (int s = 0; s < d.world && ok; ++s) {
+                // epochs only grow; compare as signed distance so that wrap-around stays harmless.  The
+                // acquire load orders the reads of the entries (by the whole CTA, after the barrier) behind it.
+                while ((int32_t)(ld_acquire_sys(d.flags + s) - d.epoch) < 0) {
+                    __nanosleep(100);
+                    if (globaltimer_ns() - t0 > d.timeout_ns) { ok = 0; break; }
+                }
+            }
+            if (!ok && blockIdx.x == 0) atomicAdd(d.errors, 1u);
+            arrived = ok;
+        }
+        __syncthreads();
+        if (!arrived) return;
+    }
+    // (frame, source, region) triples are dealt round-robin to the warps in chunks of 32: a warp loads 32
+    // count words in one go (most are zero: far ranks send nothing), then works through the non-empty ones.
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarp = gridDim.x * (blockDim.x >> 5);
+    const uint32_t per_frame = (uint32_t)d.world * d.nregion; // the count words of a frame are contiguous
+    for (int f = 0; f < d.nf; ++f) {
+        uint32_t* cnt = d.cnt + (size_t)f * d.cnt_frame_stride;
+        const uint32_t* inbox = d.inbox + (size_t)f * d.inbox_frame_stride;
+        uint32_t* band = d.band[f];
+        for (uint32_t c0 = warp * 32u; c0 < per_frame; c0 += nwarp * 32u) {
+            const uint32_t c = c0 + lane;
+            uint32_t* word = cnt + c;
+            const uint32_t mine = (c < per_frame) ? min(__ldcg(word), ROUTE_REGION) : 0u; // written by a peer: read at L2
+            if (mine) *word = 0u;
+            uint32_t todo = __ballot_sync(0xFFFFFFFFu, mine != 0u);
+            while (todo) {
+                const int r = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                const uint32_t n = __shfl_sync(0xFFFFFFFFu, mine, r);
+                const uint32_t* seg = inbox + (size_t)(c0 + (uint32_t)r) * ROUTE_REGION;
+                for (uint32_t i0 = 0; i0 < n; i0 += 256u) { // 8 loads in flight per lane: the loop is latency-bound
+                    uint32_t e[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t i = i0 + (uint32_t)j * 32u + lane;
+                        e[j] = i < n ? __ldcg(seg + i) : 0xFFFFFFFFu;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (e[j] >= d.band_cells) continue;
+                        band_add(band, e[j], CELLS == CELL_F16, d.wrap_w, d.halo, d.pitch);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- bucket sort by tile ----------------------------------------------------------------------------
+
+struct SortGrid {
+    int shift_x, shift_y; // tile = 2^shift_x x 2^shift_y texels
+    uint32_t tiles_x, ntiles;
+    uint32_t width, height;
+};
+
+__device__ __forceinline__ uint32_t home_tile(float2 p, const SortGrid& sg) {
+    int32_t x = f2i32_x86(p.x), y = f2i32_x86(p.y);
+    x = max(0, min(x, (int32_t)sg.width - 1));
+    y = max(0, min(y, (int32_t)sg.height - 1));
+    return (uint32_t)(y >> sg.shift_y) * sg.tiles_x + (uint32_t)(x >> sg.shift_x);
+}
+
+__global__ void __launch_bounds__(256)
+sort_count_kernel(const float2* __restrict__ pts, uint32_t npts, SortGrid sg, uint32_t* __restrict__ counts) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npts) atomicAdd(counts + home_tile(pts[i], sg), 1u);
+}
+
+constexpr int SCAN_BLOCK = 1024;
+
+// exclusive scan of up to SCAN_BLOCK values per block; block totals to `sums`
+__global__ void __launch_bounds__(SCAN_BLOCK)
+scan_local_kernel(uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const uint32_t v = i < n ? data[i] : 0u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w, o);
+            if (lane >= o) w += t;
+        }
+        warp_tot[lane] = w; // inclusive totals
+    }
+    __syncthreads();
+    const uint32_t base = warp ? warp_tot[warp - 1] : 0u;
+    if (i < n) data[i] = base + inc - v;
+    if (threadIdx.x == SCAN_BLOCK - 1) sums[blockIdx.x] = base + inc;
+}
+
+// single block: exclusive scan of `n` block totals in place, any n
+__global__ void __launch_bounds__(SCAN_BLOCK)
+scan_sums_kernel(uint32_t* __restrict__ sums, uint32_t n) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base0 = 0; base0 < n; base0 += SCAN_BLOCK) {
+        const uint32_t i = base0 + threadIdx.x;
+        const uint32_t v = i < n ? sums[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w, o);
+                if (lane >= o) w += t;
+            }
+            warp_tot[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t carry = carry_s;
+        const uint32_t pre = (warp ? warp_tot[warp - 1] : 0u) + carry;
+        if (i < n) sums[i] = pre + inc - v;
+        __syncthreads();
+        if (threadIdx.x == SCAN_BLOCK - 1) carry_s = pre + inc;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK)
+scan_add_kernel(uint32_t* __restrict__ data, uint32_t n, const uint32_t* __restrict__ sums) {
+    const uint32_t i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    if (i < n) data[i] += sums[blockIdx.x];
+}
+
+// cursors[] holds the exclusive scan; each point claims the next slot of the tile it is in NOW and
+// takes its whole record (position, home, reset phase, original index) along.
+template <typename OffT>
+__global__ void __launch_bounds__(256)
+regroup_scatter_kernel(const float2* __restrict__ pos, const float2* __restrict__ orig,
+                       const OffT* __restrict__ offset, const uint32_t* __restrict__ perm, uint32_t npts,
+                       SortGrid sg, uint32_t* __restrict__ cursors, float2* __restrict__ pos_out,
+                       float2* __restrict__ orig_out, OffT* __restrict__ offset_out,
+                       uint32_t* __restrict__ perm_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    const float2 p = pos[i];
+    const uint32_t slot = atomicAdd(cursors + home_tile(p, sg), 1u);
+    pos_out[slot] = p;
+    orig_out[slot] = orig[i];
+    offset_out[slot] = offset[i];
+    perm_out[slot] = perm[i];
+}
+
+// A reset offset as stored: offsets >= nframes never match a frame's phase (the reference's own "already
+// reset" sentinel is age_offset == nframes, advect_points.cc:150) and are stored as all ones -- 16-bit
+// storage is only used when nframes < 65535, so the sentinel is never a valid phase.
+template <typename OffT>
+__device__ __forceinline__ OffT stored_offset(uint32_t off, uint32_t nframes) {
+    return off < nframes ? (OffT)off : (OffT)~(OffT)0;
+}
+
+// The per-point arrays in the caller's order.
+template <typename OffT>
+__global__ void __launch_bounds__(256)
+identity_order_kernel(const float2* __restrict__ pts, const uint32_t* __restrict__ offs, uint32_t npts, uint32_t nframes,
+                      float2* __restrict__ pos, float2* __restrict__ orig, OffT* __restrict__ offset,
+                      uint32_t* __restrict__ perm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    const float2 p = pts[i];
+    pos[i] = p; orig[i] = p; offset[i] = stored_offset<OffT>(offs[i], nframes); perm[i] = i;
+}
+
+__global__ void __launch_bounds__(256)
+unpermute_kernel(const float2* __restrict__ pos, const uint32_t* __restrict__ perm, uint32_t npts,
+                 float2* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npts) out[perm[i]] = pos[i];
+}
+
+// ---- multi-GPU shards chosen on the device ------------------------------------------------------------
+// Rank r simulates the points whose HOME row lies in [row_lo, row_hi).  Same truncation as the splat
+// ((int32_t) cast, splat_points.cc:144); anything outside the image goes to the nearest row.
+__device__ __forceinline__ uint32_t home_row(float2 p, uint32_t height) {
+    const float y = p.y;
+    if (!(y == y)) return 0u;                         // NaN
+    if (y >= (float)height) return height - 1u;
+    if (y <= 0.0f) return 0u;
+    return min((uint32_t)y, height - 1u);
+}
+
+__global__ void __launch_bounds__(256)
+row_histogram_kernel(const float2* __restrict__ pts, uint32_t npts, uint32_t height, uint32_t* __restrict__ rows) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x)
+        atomicAdd(rows + home_row(pts[i], height), 1u);
+}
+
+// Unordered compaction (the order of a shard does not matter: counts commute, trajectories are per point and
+// the original index travels with the point): warp-aggregated slot claims.
+template <typename OffT>
+__global__ void __launch_bounds__(256)
+select_rows_kernel(const float2* __restrict__ pts, const uint32_t* __restrict__ offs, uint32_t npts, uint32_t nframes, uint32_t height,
+                   uint32_t row_lo, uint32_t row_hi, uint32_t* __restrict__ cursor, uint32_t capacity,
+                   float2* __restrict__ pos, float2* __restrict__ orig, OffT* __restrict__ offset,
+                   uint32_t* __restrict__ perm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float2 p = make_float2(0.f, 0.f);
+    bool take = false;
+    if (i < npts) {
+        p = pts[i];
+        const uint32_t r = home_row(p, height);
+        take = r >= row_lo && r < row_hi;
+    }
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, take);
+    if (!mask) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t base = 0u;
+    if (lane == (uint32_t)(__ffs(mask) - 1)) base = atomicAdd(cursor, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(mask) - 1);
+    if (!take) return;
+    const uint32_t slot = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+    if (slot >= capacity) return;
+    pos[slot] = p; orig[slot] = p; offset[slot] = stored_offset<OffT>(offs[i], nframes); perm[slot] = i;
+}
+
+} // namespace clumpy

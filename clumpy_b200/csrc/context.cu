@@ -47,6 +47,25 @@ int minmax_fetch(clumpy_cuda_ctx* ctx, float* minval, float* maxval) {
     return CLUMPY_OK;
 }
 
+void* ctx_pinned_get(clumpy_cuda_ctx* ctx, size_t bytes) {
+    // smallest cached buffer that is large enough
+    int best = -1;
+    for (int i = 0; i < (int)ctx->pinned_cache.size(); ++i)
+        if (ctx->pinned_cache[i].second >= bytes && (best < 0 || ctx->pinned_cache[i].second < ctx->pinned_cache[best].second)) best = i;
+    if (best >= 0) {
+        void* p = ctx->pinned_cache[best].first;
+        ctx->pinned_cache.erase(ctx->pinned_cache.begin() + best);
+        return p;
+    }
+    return clumpy_cuda_host_alloc(bytes);
+}
+
+void ctx_pinned_put(clumpy_cuda_ctx* ctx, void* p, size_t bytes) {
+    if (!p) return;
+    if (ctx->pinned_cache.size() >= 16) { cudaFreeHost(p); return; }
+    ctx->pinned_cache.emplace_back(p, bytes);
+}
+
 } // namespace clumpy
 
 using namespace clumpy;
@@ -59,6 +78,8 @@ CLUMPY_API int clumpy_cuda_device_count(int* count) {
     CK(cudaGetDeviceCount(count));
     return CLUMPY_OK;
 }
+
+static int create_impl(clumpy_cuda_ctx* ctx, int device, void* stream, const cudaDeviceProp& prop);
 
 CLUMPY_API int clumpy_cuda_create(int device, void* stream, clumpy_cuda_ctx** out) {
     REQUIRE(out, "out is NULL");
@@ -80,6 +101,13 @@ CLUMPY_API int clumpy_cuda_create(int device, void* stream, clumpy_cuda_ctx** ou
     }
     clumpy_cuda_ctx* ctx = new (std::nothrow) clumpy_cuda_ctx();
     if (!ctx) { set_error("out of host memory"); return CLUMPY_ERR_NOMEM; }
+    const int rc = create_impl(ctx, device, stream, prop);
+    if (rc != CLUMPY_OK) { clumpy_cuda_destroy(ctx); return rc; } // releases whatever was created
+    *out = ctx;
+    return CLUMPY_OK;
+}
+
+static int create_impl(clumpy_cuda_ctx* ctx, int device, void* stream, const cudaDeviceProp& prop) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
@@ -100,25 +128,31 @@ CLUMPY_API int clumpy_cuda_create(int device, void* stream, clumpy_cuda_ctx** ou
     CK(cudaEventCreate(&ctx->t1));
     CK(cudaMalloc(&ctx->d_minmax, 8));
     CK(cudaMallocHost(&ctx->h_minmax, 8));
-    *out = ctx;
+    {
+        // keep what commands free in the device's default pool instead of returning it to the driver
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     return CLUMPY_OK;
 }
 
 CLUMPY_API void clumpy_cuda_destroy(clumpy_cuda_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->copy_stream);
-    cudaStreamSynchronize(ctx->aux_stream);
-    cudaStreamSynchronize(ctx->aux2_stream);
-    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
-    cudaStreamDestroy(ctx->copy_stream);
-    cudaStreamDestroy(ctx->aux_stream);
-    cudaStreamDestroy(ctx->aux2_stream);
-    cudaEventDestroy(ctx->t0);
-    cudaEventDestroy(ctx->t1);
-    cudaFree(ctx->d_minmax);
-    cudaFreeHost(ctx->h_minmax);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (cudaStream_t s : {ctx->copy_stream, ctx->aux_stream, ctx->aux2_stream})
+        if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->d_minmax) cudaFree(ctx->d_minmax);
+    if (ctx->h_minmax) cudaFreeHost(ctx->h_minmax);
+    cudaGetLastError();
+    for (auto& b : ctx->pinned_cache) cudaFreeHost(b.first);
     delete ctx;
 }
 
@@ -127,6 +161,7 @@ CLUMPY_API int clumpy_cuda_sync(clumpy_cuda_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->aux_stream));
+    CK(cudaStreamSynchronize(ctx->aux2_stream));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     return CLUMPY_OK;
 }

@@ -7,6 +7,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "clumpy_cuda.h"
 
@@ -41,6 +43,11 @@ void set_error(const char* fmt, ...);
         }                                                                                     \
     } while (0)
 
+// Device memory of a command comes from the device's stream-ordered pool (cudaMallocAsync on the context's
+// stream; clumpy_cuda_create raises the pool's release threshold so that what one command frees the next one
+// gets back without going to the driver: allocation + release were 50 ms of a 200 ms advect_points run).
+// Memory that other processes / devices map (the multi-GPU inbox) still comes from cudaMalloc.
+#define DEV_ALLOC(ctx, pp, bytes) CK(cudaMallocAsync((void**)(pp), (bytes), (ctx)->stream))
 static inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 static inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
@@ -65,9 +72,21 @@ struct clumpy_cuda_ctx {
     uint64_t launches = 0;
     uint32_t* d_minmax = nullptr; // 2 order-preserving encoded floats (min, max)
     uint32_t* h_minmax = nullptr; // pinned mirror
+    // Pinned host buffers handed back by finished commands, kept for the next one (pinning 64 MB costs
+    // ~40 ms, more than a whole 20-frame advect_points run at the C4 size); freed with the context.
+    std::vector<std::pair<void*, size_t>> pinned_cache;
 };
 
 namespace clumpy {
+
+static inline void dev_release(clumpy_cuda_ctx* ctx, void* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+void* ctx_pinned_get(clumpy_cuda_ctx* ctx, size_t bytes); // NULL on failure (error set)
+void ctx_pinned_put(clumpy_cuda_ctx* ctx, void* p, size_t bytes);
+
+// advect_points.cc:127-135 (age_offsets.cc)
+void age_offsets_host(uint32_t nframes, uint32_t npts, uint32_t* dst);
 
 // ---- min / max of a float stream, reduced on the device ------------------------------------
 int minmax_reset(clumpy_cuda_ctx* ctx);
@@ -102,34 +121,52 @@ struct SpriteRings {
 };
 int make_sprite_rings(int kernel_size, float alpha, SpriteRings* out);
 
-// ---- dense path: u8 saturating counters + replay tables (composite_dense.cu) ------------------
+// ---- group composite for half-float cells, k <= 3 (composite_group.cu) ---------------------------
 //
-// For the sprites advect_points uses (opacity 1) every ring's truncating blend f_a becomes
-// stationary after a small number of applications for ALL 256 start values (12 for k = 3, 88 at
-// most).  So a counter only has to count up to that depth: cells are bytes that saturate at
-// `cell_cap` (packed 4 per word, updated with a compare-and-swap loop), the counter image is W*H
-// bytes and stays resident in L2, and the composite pass replaces the replay loop by one lookup per
-// ring in a table of iterated blends T_r[n][d] = f_a^n(d) held in shared memory.
-struct DenseTables {
-    bool valid = false;      // false: some ring needs more than cell_cap applications -> use u32 cells
-    int kernel_size = 0;
-    int nring = 0;
-    int depth[16] = {0};     // number of table rows of ring r (0: ring has opacity 0, skipped)
-    int row0[16] = {0};      // first row of ring r; row 0 of the block is the decay table
-    int nrows = 0;
-    uint32_t cell_cap = 255; // saturation value of a cell
-    bool byte_lanes = false; // ring sums of 4 pixels fit the 4 bytes of one register
-    uint8_t* d_rows = nullptr; // nrows * 256 bytes, device
-};
-int build_dense_tables(clumpy_cuda_ctx* ctx, const SpriteRings& rings, float decay, DenseTables* out);
-void free_dense_tables(DenseTables* t);
-int launch_composite_dense(clumpy_cuda_ctx* ctx, const HistGeom& g, const DenseTables& t,
-                           const uint8_t* d_cells, int wrapx, const uint8_t* d_img_in,
-                           uint8_t* d_img_out);
+// For the sprites advect_points uses (opacity 1) every ring's truncating blend f_a becomes stationary
+// after a small number of applications for ALL 256 start values (6 / 8 / 12 for the three rings of
+// k = 3), so a frame's effect on a pixel is one lookup in a table indexed by the clamped ring counts and
+// the pixel value.  Cells are IEEE halves, two per word, updated with red.global.add.noftz.f16x2: a half
+// counts exactly to 2048 and then stays there, so it saturates by itself and never carries.
+constexpr int GC_MAX_FRAMES = 8; // frames one composite launch can cover
 
-// same pass for counters stored as half floats (fire-and-forget red.add.f16x2 on the advect side)
-int launch_composite_half(clumpy_cuda_ctx* ctx, const HistGeom& g, const DenseTables& t,
-                          const void* d_cells, int wrapx, const uint8_t* d_img_in, uint8_t* d_img_out);
+struct GroupTable {
+    bool valid = false;        // false: sprite not supported (k > 3) -> another cell type is used
+    int kernel_size = 0;
+    int depth[3] = {0, 0, 0};  // applications until ring r is stationary (0: ring absent / opacity 0)
+    int nrows = 0;             // (depth0 + 1) * (depth1 + 1) * (depth2 + 1)
+    size_t bytes = 0;          // nrows * 260 rounded up to 16
+    uint8_t* d_table = nullptr;
+};
+int build_group_table(clumpy_cuda_ctx* ctx, const SpriteRings& rings, float decay, GroupTable* out);
+void free_group_table(GroupTable* t);
+
+// One launch: for f < nf, in order, img = composite(img, cells[f]); frame f's pixels go to frame_out[f]
+// when that is non-null (frame_out[nf - 1] must be).  `cells[f]` points at padded row 0, column 0 of the
+// region: the cell of image pixel (-halo, -halo); the region must have round_up(height, 8) + 2 * halo rows
+// of `pitch` cells.  In-place (frame_out == img_in) is allowed.  zero[]: counter images this launch clears.
+// flags != NULL: wait until flags[s] has reached `epoch` for every s < nsrc (multi-GPU frame fence).
+struct GroupCompositeArgs {
+    int width = 0, height = 0;   // pixels
+    int pitch = 0;               // cells per padded row (a multiple of 4)
+    int img_pitch = 0;           // bytes per image row
+    int nf = 0;
+    const void* cells[GC_MAX_FRAMES] = {};
+    uint8_t* frame_out[GC_MAX_FRAMES] = {};
+    const uint8_t* img_in = nullptr;
+    int nzero = 0;
+    uint4* zero[GC_MAX_FRAMES] = {};
+    uint32_t zero_n16[GC_MAX_FRAMES] = {};
+    const uint32_t* flags = nullptr;
+    uint32_t epoch = 0;
+    int nsrc = 0;
+    uint32_t* errors = nullptr;
+    unsigned long long timeout_ns = 0;
+    // filled in by the launcher
+    int tiles_x = 0, ntiles = 0, vec_ok = 0;
+    float depth[3] = {0.f, 0.f, 0.f};
+};
+int launch_composite_group(clumpy_cuda_ctx* ctx, cudaStream_t stream, const GroupTable& t, GroupCompositeArgs& a);
 
 // ---- exact-order path for sparse clouds (composite_exact.cu): 64-bit cells = count + index sum ----
 bool exact_mode_supported(int kernel_size, uint64_t npts);

@@ -15,10 +15,7 @@ The host-side plan (who owns which points and rows) is plain Python and is exerc
 gloo backend in tests/test_multigpu_cpu.py; the device work goes through the C ABI
 (clumpy_cuda_advect_count / _cells / _composite_rows / _finish_frame).
 """
-import json
 import os
-import sys
-import time
 
 import numpy as np
 
@@ -48,9 +45,7 @@ def shard_indices(pts, height, world, rank, how="home_rows"):
     # same truncation as the splat (int32 cast); anything outside the image goes to the nearest row
     y = np.nan_to_num(pts[:, 1].astype(np.float64), nan=0.0, posinf=float(height), neginf=0.0)
     row = np.clip(y, 0, height - 1).astype(np.int64)
-    below = np.cumsum(np.bincount(row, minlength=height))  # points with home row <= y
-    # first row of strip r: the first row at which n*r/world points lie strictly above
-    edges = [int(np.searchsorted(below, n * r // world, side="right")) if r else 0 for r in range(world)] + [height]
+    edges = strip_edges(np.bincount(row, minlength=height), world)
     return np.nonzero((row >= edges[rank]) & (row < edges[rank + 1]))[0]
 
 
@@ -169,8 +164,18 @@ class _DeviceView:
 _TYPESTR = {1: ("|u1", "uint8"), 2: ("<f2", "float16"), 4: ("<i4", "int32")}
 
 
+def strip_edges(rows, world):
+    """Row strips of equal point count: edges[r] is the first row of strip r (edges[world] = height), from the
+    per-row point counts `rows` (Context.row_histogram or numpy.bincount)."""
+    height, n = len(rows), int(np.sum(rows, dtype=np.int64))
+    below = np.cumsum(rows, dtype=np.int64)  # points with home row <= y
+    return [int(np.searchsorted(below, n * r // world, side="right")) if r else 0 for r in range(world)] + [height]
+
+
 class ShardedAdvect:
-    """advect_points with the points of one run spread over torch.distributed ranks."""
+    """advect_points with the points of one run spread over torch.distributed ranks, the counter images summed
+    with an NCCL reduce-scatter every frame (the north star's literal design; kept as the baseline the routed
+    variant is measured against)."""
 
     def __init__(self, ctx, pts, vel, step_size, kernel_size, decay, nframes, dist, device):
         import torch
@@ -182,13 +187,11 @@ class ShardedAdvect:
         n = len(pts)
         lo, hi = shard_range(n, self.world, self.rank)
         offsets = clumpy_b200.age_offsets(nframes, n)[lo:hi]  # offsets follow the GLOBAL point index
-        # count-only cells (the exact-order cells carry local indices); rows padded so that every
+        # count-only cells (the exact-order cells carry local indices); one stream; rows padded so that every
         # rank gets a whole number of 16-row tiles
-        os.environ["CLUMPY_CUDA_CELLS"] = "f16" if kernel_size <= 3 else "u32"
-        os.environ["CLUMPY_CUDA_OVERLAP"] = "0"
-        os.environ["CLUMPY_CUDA_CELL_ROWS_MULTIPLE"] = str(CELL_ROW_MULTIPLE * self.world)
         self.adv = ctx.advect(np.ascontiguousarray(pts[lo:hi]), vel, step_size, kernel_size, decay, nframes,
-                              age_offset=offsets)
+                              age_offset=offsets, cells="count", overlap=-1,
+                              cell_rows_multiple=CELL_ROW_MULTIPLE * self.world)
         self.npts_local = hi - lo
         ptr, nbytes, pitch, rows, halo, bpc = self.adv.cells()
         typestr, tname = _TYPESTR[bpc]
@@ -242,15 +245,16 @@ class ShardedAdvect:
 
 
 class RoutedAdvect:
-    """advect_points across ranks with the splat exchange FUSED into the advect kernel: the counter
-    image is distributed by row bands and every rank's advect kernel stores each point's cell index
-    straight into the owning rank's inbox through peer-mapped memory (CUDA IPC over NVLink); see
-    include/clumpy_cuda.h "multi-GPU with the exchange fused into the advect kernel".  Per frame the
-    only collective is an all-gather of world x world entry counts, which is also the frame fence."""
+    """advect_points across ranks with the splat exchange FUSED into the advect kernel: the counter image is
+    distributed by row bands and every rank's route kernel stores each point's cell index straight into the
+    owning rank's inbox through peer-mapped memory (CUDA IPC over NVLink); see include/clumpy_cuda.h "multi-GPU
+    with the exchange fused into the advect kernel".  No collective on the data path.
 
-    def __init__(self, ctx, pts, vel, step_size, kernel_size, decay, nframes, dist, device):
+    pts: (N, 2) numpy array (ALL the points; the rank's shard is selected on the device) or a torch CUDA tensor.
+    vel: (H, W, 2) numpy array, or a torch CUDA tensor holding the whole (replicated) field, used in place."""
+
+    def __init__(self, ctx, pts, vel, step_size, kernel_size, decay, nframes, dist, device, shard="home_rows"):
         import torch
-        import clumpy_b200
         self.torch, self.dist = torch, dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         # profiling aid: one process plays rank r of w alone (CLUMPY_ROUTE_LOOPBACK=1 CLUMPY_ROUTE_LOOPBACK_AS=r/w);
@@ -259,52 +263,53 @@ class RoutedAdvect:
         if self.loopback:
             self.rank, self.world = (int(v) for v in os.environ.get("CLUMPY_ROUTE_LOOPBACK_AS", "3/8").split("/"))
         self.ctx, self.device = ctx, device
-        self.h_img, self.w_img = vel.shape[:2]
-        n = self.n_total = len(pts)
-        how = os.environ.get("CLUMPY_MULTIGPU_SHARD", "home_rows")
-        self.indices = shard_indices(pts, self.h_img, self.world, self.rank, how)
-        offsets = clumpy_b200.age_offsets(nframes, n)[self.indices]  # offsets follow the GLOBAL point index
-        os.environ["CLUMPY_CUDA_CELLS"] = "f16" if kernel_size <= 3 else "u32"  # count-only cells
-        os.environ.pop("CLUMPY_CUDA_CELL_ROWS_MULTIPLE", None)  # (the dense variant's: bands here are the library's own)
-        self.adv = ctx.advect(np.ascontiguousarray(pts[self.indices]), vel, step_size, kernel_size, decay, nframes,
-                              age_offset=np.ascontiguousarray(offsets))
-        sizes = torch.zeros(self.world, dtype=torch.int64, device=device)
-        sizes[self.rank] = len(self.indices)
-        if self.world > 1 and not self.loopback:
-            dist.all_reduce(sizes)
-        self.shard_sizes = [int(v) for v in sizes.tolist()]
+        self.h_img, self.w_img = int(vel.shape[0]), int(vel.shape[1])
+        self.n_total = n = int(pts.shape[0])
+        d_pts = pts if torch.is_tensor(pts) else torch.from_numpy(np.ascontiguousarray(pts, np.float32)).to(device, non_blocking=True)
+        self._vel = vel  # a device field is used in place: keep it alive
+        torch.cuda.current_stream().synchronize()
+        if shard == "home_rows":
+            # strips of equal point count, from the row histogram of the whole cloud: every rank computes the
+            # same edges from the same points, so nothing is exchanged
+            rows = ctx.row_histogram(d_pts.data_ptr(), self.h_img, npts=n)
+            edges = strip_edges(rows, self.world)
+            self.shard_sizes = [int(rows[edges[r]:edges[r + 1]].sum()) for r in range(self.world)]
+            lo, hi = edges[self.rank], edges[self.rank + 1]
+            points_arg, npts_arg, rows_arg = d_pts.data_ptr(), n, ((lo, hi) if hi > lo else (self.h_img, self.h_img + 1))
+            offsets = None  # computed by the library for the whole list while it uploads
+        else:  # contiguous index ranges (tests: everything travels through the inboxes)
+            import clumpy_b200
+            lo, hi = shard_range(n, self.world, self.rank)
+            self.shard_sizes = [shard_range(n, self.world, r)[1] - shard_range(n, self.world, r)[0] for r in range(self.world)]
+            points_arg, npts_arg, rows_arg = d_pts[lo:hi].contiguous().data_ptr(), hi - lo, None
+            self._index_base = lo
+            offsets = np.ascontiguousarray(clumpy_b200.age_offsets(nframes, n)[lo:hi])
+        vel_arg = vel.data_ptr() if torch.is_tensor(vel) else vel
+        self.adv = ctx.advect(points_arg, vel_arg, step_size, kernel_size, decay, nframes, age_offset=offsets,
+                              npts=npts_arg, width=self.w_img, height=self.h_img, cells="count", shard_rows=rows_arg)
+        self.sharded_by_rows = rows_arg is not None
         capacity = max(1, max(self.shard_sizes))
         inbox, _ = self.adv.route_begin(self.rank, self.world, capacity)
-        # exchange CUDA IPC handles of the inboxes and map the peers'
-        if self.loopback:
+        # exchange CUDA IPC handles of the inboxes (64 bytes each, over NCCL) and map the peers'
+        if self.loopback or self.world == 1:
             self.peer_ptrs = [inbox] * self.world
         else:
-            handles = [None] * self.world
-            dist.all_gather_object(handles, ctx.ipc_export(inbox))
-            self.peer_ptrs = [inbox if r == self.rank else ctx.ipc_open(handles[r]) for r in range(self.world)]
+            mine = torch.frombuffer(bytearray(ctx.ipc_export(inbox)), dtype=torch.uint8).to(device)
+            handles = torch.empty((self.world, 64), dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(handles, mine)
+            handles = handles.cpu().numpy()
+            self.peer_ptrs = [inbox if r == self.rank else ctx.ipc_open(handles[r].tobytes()) for r in range(self.world)]
         self.adv.route_peers(self.peer_ptrs)
-        self.counts_all = torch.zeros((self.world, self.world), dtype=torch.int32, device=device)
         self.y0, self.y1 = self.adv.owned_rows()
-        self._counts_view = {}
-        dist.barrier()
+        if self.world > 1 and not self.loopback:
+            dist.barrier()
 
     def step(self, count=1):
-        torch, dist = self.torch, self.dist
-        if os.environ.get("CLUMPY_MULTIGPU_FENCE", "device") == "device":
-            # fence on the device (epoch flags in peer memory): one C call enqueues all the frames
-            self.adv.route_steps(count)
-            return
-        for _ in range(count):  # fence = NCCL all-gather of the entry counts, one round trip per frame
-            ptr = self.adv.route()
-            mine = self._counts_view.get(ptr)
-            if mine is None:
-                mine = torch.as_tensor(_DeviceView(ptr, (self.world,), "<i4"), device=self.device)
-                self._counts_view[ptr] = mine
-            if self.world > 1:
-                dist.all_gather_into_tensor(self.counts_all, mine)  # also the frame fence
-            else:
-                self.counts_all[0].copy_(mine)
-            self.adv.drain(self.counts_all.data_ptr())
+        self.adv.route_steps(count)  # fence on the device (epoch flags in peer memory): one call enqueues all the frames
+
+    def record(self, count, dst, frame_stride):
+        """step(count); this rank's rows of every frame are copied to the pinned tensor / array `dst`."""
+        self.adv.route_record(count, dst.data_ptr() if self.torch.is_tensor(dst) else dst, frame_stride)
 
     band_image = ShardedAdvect.band_image
     gather_image = ShardedAdvect.gather_image
@@ -312,14 +317,20 @@ class RoutedAdvect:
     def points(self):
         """All positions in the caller's order (numpy), gathered from the shards."""
         torch, dist = self.torch, self.dist
-        mine = self.adv.points()
-        if self.world == 1:
-            return mine
+        if self.sharded_by_rows:
+            mine, index = self.adv.points_indexed()
+        else:
+            mine = self.adv.points()
+            index = np.arange(self._index_base, self._index_base + len(mine), dtype=np.uint32)
+        if self.world == 1 or self.loopback:
+            out = np.empty((self.n_total, 2), dtype=np.float32)
+            out[index] = mine
+            return out
         cap = max(self.shard_sizes)
         pos = torch.zeros((cap, 2), dtype=torch.float32, device=self.device)
         idx = torch.zeros((cap,), dtype=torch.int64, device=self.device)
         pos[:len(mine)] = torch.from_numpy(mine).to(self.device)
-        idx[:len(mine)] = torch.from_numpy(self.indices).to(self.device)
+        idx[:len(mine)] = torch.from_numpy(index.astype(np.int64)).to(self.device)
         all_pos = torch.empty((self.world, cap, 2), dtype=torch.float32, device=self.device)
         all_idx = torch.empty((self.world, cap), dtype=torch.int64, device=self.device)
         dist.all_gather_into_tensor(all_pos, pos)
@@ -335,155 +346,15 @@ class RoutedAdvect:
         timeouts = self.adv.route_errors()
         if self.world > 1 and not self.loopback:
             self.dist.barrier()  # nobody may still be writing into an inbox that is about to go away
-        if timeouts:
-            raise RuntimeError(f"rank {self.rank}: {timeouts} frame fences timed out (a peer stopped publishing)")
         for r, p in enumerate(self.peer_ptrs):
-            if r != self.rank and p and not self.loopback:
+            if r != self.rank and p and not self.loopback and self.world > 1:
                 self.ctx.ipc_close(p)
         self.adv.close()
+        if timeouts:
+            raise RuntimeError(f"rank {self.rank}: {timeouts} frame fences timed out (a peer stopped publishing)")
 
 
 def make_sharded(kind, *a, **kw):
     """kind: "routed" (exchange fused into the advect kernel, default) or "dense" (counter images
     summed with an NCCL reduce-scatter)."""
     return (RoutedAdvect if kind == "routed" else ShardedAdvect)(*a, **kw)
-
-
-def bench_multi(args, cfg, workload, metric, unit):
-    """bench.py body for --gpus N > 1 (launched by torch.distributed.run, one rank per GPU)."""
-    import torch
-    import torch.distributed as dist
-    import clumpy_b200
-    from bench import ALGO_BYTES_PER_PIXEL_FRAME, ALGO_BYTES_PER_POINT_STEP, ClockSampler, measured_peaks, synth_points
-
-    t_start = time.perf_counter()
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    device = torch.device("cuda", local_rank)
-    dist.init_process_group("nccl", device_id=device)
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    ctx = clumpy_b200.Context(local_rank, stream.cuda_stream)
-    n, w, h = cfg["npts"], cfg["width"], cfg["height"]
-    # development aid (never set by the driver): CLUMPY_BENCH_ROWS_DIV=d runs 1/d of the workload --
-    # the top h/d rows of the field and n/d points -- so that `world` ranks see the per-rank working
-    # set of a (world * d)-rank run of the full workload.  The JSON line says so in config.workload.
-    rows_div = int(os.environ.get("CLUMPY_BENCH_ROWS_DIV", "1"))
-    if rows_div > 1:
-        n, h = n // rows_div, h // rows_div
-        workload = f"SCALED 1/{rows_div} (development run, not the benchmark): {n} points on {w}x{h}; " + workload
-    K, W = args.steps, args.warmup
-    hbm_peak, peak_src = measured_peaks()
-
-    # points come from the same seeded recipe on every rank and are sliced by the sharded run
-    # the (replicated) field: simplex + curl row-sharded across the ranks, bands all-gathered over NCCL
-    d_vel = sharded_simplex_curl(ctx, w, h, cfg["amplitude"], cfg["frequency"] / rows_div, cfg["seed"], dist, device)
-    vel = torch.empty((h, w, 2), dtype=torch.float32).pin_memory()
-    vel.copy_(d_vel)
-    torch.cuda.synchronize()
-    del d_vel
-    pts = synth_points(n, w, h)
-
-    def note(msg):  # progress on stderr (CLUMPY_BENCH_VERBOSE=1)
-        if os.environ.get("CLUMPY_BENCH_VERBOSE") == "1":
-            print(f"[bench rank {rank} +{time.perf_counter() - t_start:.2f}s] {msg}", file=sys.stderr, flush=True)
-
-    kind = os.environ.get("CLUMPY_MULTIGPU", "routed")
-    note("inputs ready")
-    run = make_sharded(kind, ctx, pts, vel.numpy(), cfg["step_size"], cfg["kernel_size"], cfg["decay"], cfg["nframes"],
-                       dist, device)
-    # CLUMPY_BENCH_NO_CLOCKS=1 (A/B runs): nvidia-smi polling GPU 0 every 50 ms is not free for rank 0
-    sampler = ClockSampler(local_rank) if rank == 0 and os.environ.get("CLUMPY_BENCH_NO_CLOCKS") != "1" else None
-    note("sharded run set up")
-    run.step(W)
-    note("warm-up enqueued")
-    dist.barrier()
-    torch.cuda.synchronize()
-    note("warm-up done")
-    launches0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    run.step(K)
-    e1.record(stream)
-    dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)  # slowest rank
-    ms = float(ms.item())
-    note(f"timed region done: {ms / K:.4f} ms per frame")
-    launches = ctx.launch_count() - launches0
-    value = n * K / (ms * 1e-3)
-
-    # per-rank kernel times (CUDA events around every kernel; the drain includes the wait for the peers)
-    kernel_ms = None
-    if kind == "routed" and os.environ.get("CLUMPY_MULTIGPU_FENCE", "device") == "device":
-        t = torch.tensor(run.adv.route_profile(50), device=device)
-        allt = torch.empty((world, 3), device=device)
-        dist.all_gather_into_tensor(allt, t)
-        kernel_ms = {"route": allt[:, 0].tolist(), "drain_incl_wait": allt[:, 1].tolist(), "composite": allt[:, 2].tolist(),
-                     "points_per_rank": run.shard_sizes}
-
-    note(f"kernel profile done: {kernel_ms}")
-    # e2e: every rank also copies its band of each recorded frame to pinned host memory
-    y0, y1 = run.y0, run.y1
-    host_band = [torch.empty((max(1, y1 - y0), w), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    nrec = max(1, K // 2)
-    dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    run2 = make_sharded(kind, ctx, pts, vel.numpy(), cfg["step_size"], cfg["kernel_size"], cfg["decay"], nrec, dist, device)
-    note("e2e: second run set up")
-    run2.step(nrec)
-    note("e2e: warm-up frames enqueued")
-    for f in range(nrec):
-        run2.step(1)
-        if y1 > y0:
-            host_band[f & 1][:y1 - y0].copy_(run2.band_image(), non_blocking=True)
-        if f % 50 == 0:
-            note(f"e2e: recorded frame {f} enqueued")
-    note("e2e: all frames enqueued")
-    torch.cuda.synchronize()
-    note(f"e2e: device idle, fence time-outs so far: {run2.adv.route_errors() if kind == 'routed' else 0}")
-    dist.barrier()
-    dt = torch.tensor([time.perf_counter() - t0], device=device)
-    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    dt = float(dt.item())
-    run2.close()
-    run.close()
-    clocks = sampler.stop() if sampler else None
-    if rank == 0:
-        e2e_steps = 2 * nrec
-        line = {
-            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32+u8", "data": "synthetic",
-            "config": {"workload": workload, "frames_per_s": K / (ms * 1e-3),
-                       "parallelism": (f"points sharded x{world} by home row, field replicated, counter image distributed by "
-                                       "row bands; a rank's route kernel (up to 4 frames per launch) counts the points "
-                                       "that land in its own band directly and stores the others' cell indices into the "
-                                       "band owners' inboxes through peer memory (NVLink); device-side frame fence (epoch "
-                                       "flags in peer memory); drain + band composite per rank on side streams; no "
-                                       "collective on the data path") if kind == "routed" else
-                                      (f"points sharded x{world}, field replicated, per-frame NCCL reduce-scatter of the "
-                                       "f16 counter image by row bands + halo all-gather, band composite per rank"),
-                       "l2": "inputs larger than L2, no flush: per rank and ring period (8 frames) the frames touch positions + "
-                             "phases (21 MB at 8 ranks), the rank's part of the field (~35-60 MB), 8 band buffers "
-                             "(8 x 8.6 MB), the image band and the inbox slots -- ~160 MB at 8 ranks, more with fewer "
-                             "ranks -- against 126 MB of L2"},
-            "clocks": clocks,
-            "e2e": {"value": n * e2e_steps / dt, "unit": unit,
-                    "h2d_bytes_per_step": (n * 12 + world * w * h * 8) / e2e_steps, "d2h_bytes_per_step": nrec * w * h / e2e_steps,
-                    "steps": e2e_steps, "seconds": dt,
-                    "what": "per rank: H2D of its point shard + the whole field, sort, frames, D2H of its row band of "
-                            "every recorded frame to pinned memory"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "whole step (all ranks)", "peak": hbm_peak * world, "unit": "GB/s",
-                         "achieved": (n * ALGO_BYTES_PER_POINT_STEP + w * h * ALGO_BYTES_PER_PIXEL_FRAME) / (ms / K * 1e-3) / 1e9,
-                         "frac": (n * ALGO_BYTES_PER_POINT_STEP + w * h * ALGO_BYTES_PER_PIXEL_FRAME) / (ms / K * 1e-3) / 1e9 / (hbm_peak * world),
-                         "traffic": None, "peak_source": peak_src, "per_rank_kernel_ms": kernel_ms},
-            "cpu_baseline": None,
-        }
-        print(json.dumps(line))
-    ctx.close()
-    dist.destroy_process_group()
-    return 0

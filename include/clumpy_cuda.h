@@ -66,6 +66,14 @@ int clumpy_cuda_timer_stop(clumpy_cuda_ctx* ctx, float* elapsed_ms); /* synchron
 /* Number of kernels this library has launched on `ctx` since creation. */
 int clumpy_cuda_launch_count(clumpy_cuda_ctx* ctx, uint64_t* launches);
 
+/* Measurement aid: throughput of the reductions the splat is made of.  Issues `nupdates`
+ * fire-and-forget reductions per launch -- op 0: red.global.add.noftz.f16x2 on half cells, op 1:
+ * red.global.add.u32 -- on a scratch region of `region_bytes`; pattern 0: uniform random cells, 1: all on
+ * `hot_cells` cells, 2: update i near cell i * ncells / nupdates (a cloud stored in tile order).  Returns the
+ * mean device time of one launch over `iters` launches (CUDA events, clears excluded).  Synchronises. */
+int clumpy_cuda_atomic_peak(clumpy_cuda_ctx* ctx, int op, int pattern, size_t region_bytes,
+                            uint64_t nupdates, uint32_t hot_cells, int iters, float* ms_per_launch);
+
 /* ---- generate_simplex ------------------------------------------------------------------ */
 
 /* Host helper: the 256-entry permutation of commands/generate_simplex.cc:241-280. */
@@ -155,22 +163,63 @@ int clumpy_cuda_advect_begin(clumpy_cuda_ctx* ctx, const float* pts_host, uint32
                              float step_size, int kernel_size, float decay, int wrapx,
                              uint32_t nframes, const uint32_t* age_offset, clumpy_advect** out);
 
+/* The same set-up with everything spelled out (the device-resident pipeline).  Points, field and
+ * offsets may already be on the device; a device field is used IN PLACE (it must outlive the run), which is how
+ * `generate_simplex_dev -> curl_2d_dev -> advect` chains without a host round trip.  shard_row_lo < shard_row_hi
+ * keeps only the points whose HOME row (the row of their initial position, truncated like the splat) lies in
+ * [lo, hi): the multi-GPU shards, selected on the device (see clumpy_cuda_row_histogram).  age_offset values
+ * >= nframes mean "never resets" (the reference's own sentinel, advect_points.cc:150).  Options replace the
+ * CLUMPY_CUDA_* environment switches of round 1 (which remain as overrides for A/B runs): 0 = automatic. */
+#define CLUMPY_CELLS_AUTO 0   /* sparse cloud: exact-order 64-bit cells; else the count-only type            */
+#define CLUMPY_CELLS_COUNT 1  /* count-only cells: half floats for k <= 3, 32-bit otherwise (multi-GPU runs) */
+#define CLUMPY_CELLS_F16 2
+#define CLUMPY_CELLS_U32 3
+#define CLUMPY_CELLS_EXACT 4
+typedef struct clumpy_advect_desc {
+    uint32_t size;                 /* sizeof(clumpy_advect_desc) */
+    const float* pts;              /* (npts, 2) float32 */
+    uint32_t npts;
+    int pts_on_device;
+    const float* vel;              /* (height, width, 2) float32 */
+    int vel_on_device;
+    uint32_t width, height;
+    float step_size;
+    int kernel_size;
+    float decay;                   /* non-negative; negative-decay mode is wrapx = 1 */
+    int wrapx;
+    uint32_t nframes;
+    const uint32_t* age_offset;    /* npts values indexed like pts, or NULL: clumpy_cuda_age_offsets */
+    int age_on_device;
+    uint32_t shard_row_lo, shard_row_hi;
+    int cells;                     /* CLUMPY_CELLS_* */
+    int overlap;                   /* composites on a side stream: 0 auto, 1 on, -1 off */
+    int fuse;                      /* simulation frames per launch: 0 auto, 1 .. 8 */
+    int regroup;                   /* frames between regroups by tile: 0 auto, -1 never */
+    int cell_rows_multiple;        /* dense multi-GPU variant: padded counter rows a multiple of this */
+} clumpy_advect_desc;
+int clumpy_cuda_advect_begin_ex(clumpy_cuda_ctx* ctx, const clumpy_advect_desc* desc, clumpy_advect** out);
+
+/* rows_host[y] = number of points whose home row is y (y < height), counted on the device; pts may be a host
+ * or a device pointer.  Multi-GPU callers cut the image into strips of equal point count with it. */
+int clumpy_cuda_row_histogram(clumpy_cuda_ctx* ctx, const float* pts, uint32_t npts, int pts_on_device,
+                              uint32_t height, uint32_t* rows_host);
+
 /* Advances `count` simulation frames (commands/advect_points.cc:139-176 without the file write):
- * Euler step + reset of every point, u8 decay, splat.  Asynchronous; no host copies. */
+ * Euler step + reset of every point, u8 decay, splat.  Asynchronous; no host copies.  Frames are run in
+ * groups of up to 8: one advect launch (positions stay in registers) + one composite launch per group. */
 int clumpy_cuda_advect_step(clumpy_advect* adv, uint32_t count);
 
-/* Like clumpy_cuda_advect_step, but brackets every kernel with CUDA events on the context's stream
- * and returns the mean device time per frame (ms) of the advect+count kernel, the composite kernel
- * and the counter clear.  Synchronises.  Used by bench.py for the roofline of the dominant kernel. */
-int clumpy_cuda_advect_profile(clumpy_advect* adv, uint32_t count, float* advect_ms,
-                               float* composite_ms, float* clear_ms);
+/* Like clumpy_cuda_advect_step, and every one of the `count` frames is copied to dst_host + i * frame_stride
+ * (height * width u8 each) on the context's copy stream while later frames are simulated.  dst_host should be
+ * pinned.  clumpy_cuda_advect_wait_frames waits for the copies. */
+int clumpy_cuda_advect_record(clumpy_advect* adv, uint32_t count, uint8_t* dst_host, size_t frame_stride);
 
-/* clumpy_cuda_advect_step advances up to 4 frames per advect launch (positions stay in registers;
- * CLUMPY_CUDA_FUSE=1 disables).  This runs `groups` such launches as the pipeline runs them --
- * composites of the previous group sharing the GPU -- and returns the mean duration of one launch
- * (CUDA events around the launch alone) and the frames it covers.  Synchronises. */
-int clumpy_cuda_advect_profile_fused(clumpy_advect* adv, uint32_t groups, float* launch_ms,
-                                     uint32_t* frames_per_launch);
+/* The two stages of the pipeline, each timed with CUDA events around its launch on the stream it runs on, over
+ * `groups` full groups: mean ms per launch of the advect kernel and of the composite work, and the frames one
+ * launch covers.  serial = 0: as the pipeline runs them (the composite of one group shares the GPU with the
+ * advect launch of the next); serial = 1: each kernel alone on the GPU.  Synchronises.  bench.py's roofline. */
+int clumpy_cuda_advect_profile_stages(clumpy_advect* adv, uint32_t groups, int serial, float* advect_ms,
+                                      float* composite_ms, uint32_t* frames_per_launch);
 
 /* ---- one simulation frame split at its exchange point (multi-GPU) ------------------------------
  * Points advect independently, so they are sharded across GPUs, each with the whole velocity field.
@@ -201,23 +250,31 @@ int clumpy_cuda_advect_finish_frame(clumpy_advect* adv);
  * several GPUs (points advect independently, :144-153; the splat, splat_points.cc:118-161, is the one
  * thing they share).  The counter image is distributed by bands of chunk = round_up(ceil(H / world), 16)
  * padded rows (band g on GPU g, the last band also takes the padding rows) and never exists as a
- * whole.  The route kernel advects this GPU's points, counts the ones that land in its own band
- * straight into its band buffer and stores every other point's cell index (4 bytes) into the inbox of
- * the GPU that owns the cell's band -- and of the neighbouring band when the row lies within the
- * sprite's reach of the edge -- through peer-mapped memory (NVLink / NVSwitch stores from inside the
- * kernel).  A drain kernel counts the inbox into the band buffer; the band's image rows are then
- * composited as on one GPU.  Best with shards by HOME ROW (clumpy_b200/multigpu.py shard_indices):
- * most points then never leave their GPU.
+ * whole.  Frames run in GROUPS of up to 8.  Per group and GPU:
+ *   route kernel      advects this GPU's points through the group (positions stay in registers), counts the
+ *                     ones that land in its own band straight into the frame's band buffer and stores every
+ *                     other point's cell index (4 bytes) into the inbox of the GPU that owns the cell's band --
+ *                     and of the neighbouring band when the row lies within the sprite's reach of the edge --
+ *                     through peer-mapped memory (NVLink / NVSwitch stores from inside the kernel).  No barrier
+ *                     and no fence inside the frame loop; at the end a CTA fences its remote stores and takes
+ *                     a ticket, and the CTA that takes the last ticket stores the group's EPOCH into a flag
+ *                     per source in every peer's memory.
+ *   drain kernel      waits for every source's epoch (bounded: CLUMPY_ROUTE_TIMEOUT_MS, default 2000; a time-out
+ *                     makes every later call on the run fail with CLUMPY_ERR_STATE), counts the inbox entries
+ *                     of the group's frames into the band buffers.
+ *   group composite   the band's image rows through the frames of the group (composite_group.cu); also zeroes
+ *                     the band buffers of the group before.
+ * No host-side collective, no NCCL on the data path: a whole run is enqueued without synchronisation.
+ * Best with shards by HOME ROW (desc.shard_row_lo / _hi): most points then never leave their GPU.
  *
- *   set-up:   advect_begin with this rank's points (count-only cells: CLUMPY_CUDA_CELLS=f16|u32)
+ *   set-up:   advect_begin_ex with this rank's shard, desc.cells = CLUMPY_CELLS_COUNT
  *             -> route_begin (allocates this rank's inbox; export it with clumpy_cuda_ipc_export,
  *             exchange the handles, open the peers' with clumpy_cuda_ipc_open -- or, for several
- *             ranks on one GPU in one process, pass the device pointers themselves) -> route_peers
- *   frames:   route_steps(count)                       fence on the device, nothing else to call
- *        or:  route -> any collective on the context's stream that all ranks enter -> drain
+ *             ranks in one process, pass the device pointers themselves) -> route_peers
+ *   frames:   route_steps(count) / route_record(count, ...)
  *
- * `capacity` = point count of the largest shard (the same value on every rank).  Inboxes, band
- * buffers and fence tickets are rings of 8 frames, so a GPU may run a few frames ahead of a peer. */
+ * `capacity` = point count of the largest shard (the same value on every rank).  Every rank must run the same
+ * sequence of frame counts (groups are cut at the same frames everywhere). */
 #define CLUMPY_IPC_HANDLE_BYTES 64
 int clumpy_cuda_ipc_export(clumpy_cuda_ctx* ctx, const void* dptr, void* handle64);
 int clumpy_cuda_ipc_open(clumpy_cuda_ctx* ctx, const void* handle64, void** dptr);
@@ -225,25 +282,18 @@ int clumpy_cuda_ipc_close(clumpy_cuda_ctx* ctx, void* dptr);
 int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int world, uint32_t capacity,
                                    void** inbox_dev, size_t* inbox_bytes);
 int clumpy_cuda_advect_route_peers(clumpy_advect* adv, void* const* peer_inbox);
-int clumpy_cuda_advect_route(clumpy_advect* adv, void** counts_dev);
-int clumpy_cuda_advect_drain(clumpy_advect* adv, const uint32_t* counts_all_dev);
 int clumpy_cuda_advect_owned_rows(clumpy_advect* adv, uint32_t* row0, uint32_t* nrows);
-
-/* `count` frames with the fence on the DEVICE: the CTAs of the route kernel that stored into a peer's
- * inbox fence those stores and add themselves to the frame's ticket; an extra last CTA waits for the
- * ticket and stores the frame's epoch into a flag per source in every peer's memory; the drain kernel
- * waits for every source's epoch before it reads that source's entries (bounded wait: ~2 s, then the
- * source is skipped and counted in route_errors, so a dead peer cannot hang the GPU).  One route
- * launch covers up to 4 frames; drains and composites run on side streams.  All `count` frames are
- * enqueued by the one call, with no host synchronisation and no NCCL on the data path.
- * clumpy_cuda_advect_route / _drain are the one-frame variant for callers that fence themselves
- * (counts_dev / counts_all_dev are kept for source compatibility: world zeros / ignored). */
 int clumpy_cuda_advect_route_steps(clumpy_advect* adv, uint32_t count);
-/* route_steps with CUDA events around every kernel: mean device time per frame (ms) of the route
- * kernel, the drain kernel (includes the wait for the slowest peer) and the band composite.  Every
- * rank calls it with the same count.  Synchronises. */
-int clumpy_cuda_advect_route_profile(clumpy_advect* adv, uint32_t count, float* route_ms,
-                                     float* drain_ms, float* composite_ms);
+/* route_steps, and this rank's rows (clumpy_cuda_advect_owned_rows) of every one of the `count` frames are
+ * copied to dst_host + i * frame_stride on the copy stream (each GPU over its own PCIe link). */
+int clumpy_cuda_advect_route_record(clumpy_advect* adv, uint32_t count, uint8_t* dst_host, size_t frame_stride);
+/* `groups` groups launched one by one with CUDA events around every kernel: mean device time per GROUP (ms) of
+ * the route kernel, the drain kernel (includes the wait for the slowest peer) and the band composite, and the
+ * frames per group.  Every rank calls it with the same arguments.  Synchronises. */
+int clumpy_cuda_advect_route_profile(clumpy_advect* adv, uint32_t groups, float* route_ms,
+                                     float* drain_ms, float* composite_ms, uint32_t* frames_per_group);
+/* Fence time-outs seen so far.  Synchronises.  (Any non-zero count also fails route_steps / read_image /
+ * wait_frames with CLUMPY_ERR_STATE.) */
 int clumpy_cuda_advect_route_errors(clumpy_advect* adv, uint32_t* errors);
 
 /* Device address of the current framebuffer (height * width u8), for callers that gather row
@@ -252,6 +302,8 @@ int clumpy_cuda_advect_image_dev(clumpy_advect* adv, void** img_dev);
 
 /* Number of simulation frames done so far; frames [nframes, 2*nframes) are the recorded ones. */
 int clumpy_cuda_advect_simframe(clumpy_advect* adv, uint32_t* simframe);
+/* Number of points this run simulates (the shard's size when desc.shard_row_* selected one). */
+int clumpy_cuda_advect_npts(clumpy_advect* adv, uint32_t* npts);
 
 /* Enqueues a device->host copy of the current framebuffer (height*width u8) on the context's
  * copy stream, ordered after the steps issued so far; later steps do not wait for it unless they
@@ -263,6 +315,8 @@ int clumpy_cuda_advect_wait_frames(clumpy_advect* adv);
  * in the caller's original point order, and the current framebuffer.  Both synchronise. */
 int clumpy_cuda_advect_read_points(clumpy_advect* adv, float* out_host);
 int clumpy_cuda_advect_read_image(clumpy_advect* adv, uint8_t* out_host);
+/* Shards: positions in storage order + the index each point had in the caller's list (npts of each). */
+int clumpy_cuda_advect_read_points_indexed(clumpy_advect* adv, float* pos_host, uint32_t* index_host);
 
 int clumpy_cuda_advect_end(clumpy_advect* adv);
 

@@ -235,6 +235,7 @@ def ref():
                                         C.POINTER(C.c_double)]
         R.ref_exec.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p)]
         R.ref_exec.restype = C.c_int
+        R.ref_std_age_offsets.argtypes = [C.c_uint32, C.c_uint32, _u32p]
         _REF = R
     return _REF
 
@@ -252,6 +253,13 @@ def ref_splat_disks(pts, width, height, alpha, kernel_size, wrapx=False, img=Non
     ref().ref_splat_disks(_ptr(pts, _f32p), len(pts), width, height, _ptr(img, _u8p), alpha,
                           kernel_size, int(wrapx))
     return img
+
+
+def ref_std_age_offsets(nframes, npts):
+    """advect_points.cc:127-135 through <random> itself (std::mt19937 + std::uniform_int_distribution)."""
+    out = np.empty(npts, np.uint32)
+    ref().ref_std_age_offsets(nframes, npts, _ptr(out, _u32p))
+    return out
 
 
 def ref_simplex2(seed, xy):

@@ -16,6 +16,7 @@
 #include <glm/gtc/type_precision.hpp>
 
 #include <cstdint>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -59,6 +60,15 @@ SHIM_API void ref_simplex2_many(int64_t seed, const double* xy, uint32_t n, doub
     open_simplex_noise(seed, &ctx);
     for (uint32_t i = 0; i < n; ++i) out[i] = open_simplex_noise2(ctx, xy[2 * i], xy[2 * i + 1]);
     open_simplex_noise_free(ctx);
+}
+
+// The reset offsets exactly as commands/advect_points.cc:127-135 draws them: <random> itself (the
+// distribution's algorithm is the host library's, not the standard's), for pinning the restatements.
+SHIM_API void ref_std_age_offsets(uint32_t nframes, uint32_t npts, uint32_t* out) {
+    std::mt19937 generator;
+    generator.seed(0);
+    std::uniform_int_distribution<> get_age_offset(0, (int)(nframes - 1));
+    for (uint32_t i = 0; i < npts; ++i) out[i] = (uint32_t)get_age_offset(generator);
 }
 
 // Runs `clumpy <name> argv...` in-process; returns the exit code main_clumpy.cc:59 would produce,

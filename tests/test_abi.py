@@ -52,6 +52,11 @@ def test_age_offsets_match_oracle_and_goldens(oracle_mod, golden):
     for nframes in (1, 2, 3, 240, 1000, 65537):
         a = clumpy_b200.age_offsets(nframes, 5000)
         assert np.array_equal(a, oracle_mod.age_offsets(nframes, 5000)), nframes
+    # the library draws a whole generator block at a time and only falls back to draw-by-draw when a block
+    # contains a rejection candidate: exercise block boundaries, ragged tails and rejection-heavy ranges
+    for nframes, n in ((1000, 624), (1000, 625), (1000, 1 << 20), (1000003, 300001), (1500000000, 300000),
+                       (2**31 - 1, 200000), (2**30 + 7, 200000), (2**31, 100000)):
+        assert np.array_equal(clumpy_b200.age_offsets(nframes, n), oracle_mod.age_offsets(nframes, n)), (nframes, n)
 
 
 def test_simplex_perm_matches_oracle(oracle_mod, golden):

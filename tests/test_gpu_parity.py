@@ -224,10 +224,11 @@ def check_exact_order(frames, ref, k):
         assert np.array_equal(frames, ref)
 
 
-@pytest.mark.parametrize("cells", ["f16", "u8", "u32", "exact"])
+@pytest.mark.parametrize("cells", ["f16", "u32", "exact"])
 @pytest.mark.parametrize("name", ["k1", "k3", "k5", "k7", "k3_wrap", "k1_decay0"])
 def test_advect_golden_every_cell_type(ctx, golden, monkeypatch, cells, name):
-    """The same fixtures through each accumulator type (CLUMPY_CUDA_CELLS forces it)."""
+    """The same fixtures through each accumulator type (CLUMPY_CUDA_CELLS forces it; half cells exist for
+    k <= 3 only, larger sprites asked for them get 32-bit cells)."""
     monkeypatch.setenv("CLUMPY_CUDA_CELLS", cells)
     c = golden["meta"][f"advect_{name}"]
     adv = golden["advect"]
@@ -287,7 +288,7 @@ def test_advect_dense_k3_long(ctx, oracle_mod):
 def test_advect_regrouping_keeps_identity(ctx, oracle_mod, monkeypatch, regroup):
     """Periodic regrouping of the point records by tile must not change anything observable:
     trajectories (in the caller's order) stay bit-identical, frames stay within the bar."""
-    monkeypatch.setenv("CLUMPY_CUDA_REGROUP", regroup)
+    monkeypatch.setenv("CLUMPY_CUDA_REGROUP", regroup)  # (the environment switches still override the options)
     monkeypatch.setenv("CLUMPY_CUDA_CELLS", "f16")
     rng = np.random.default_rng(21)
     w, h, n = 320, 200, 70001
@@ -434,28 +435,24 @@ def test_cull_points_golden_and_edge_cases(ctx, oracle_mod, golden):
 # ---- several frames per advect launch (clumpy_cuda_advect_step groups up to 4) --------------------------------
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cells", ["auto", "f16", "u8", "u32", "exact"])
-@pytest.mark.parametrize("k,decay,nframes,overlap", [(3, 0.97, 7, "1"), (1, 0.9, 5, "0"), (5, -0.95, 6, "1"), (3, 0.0, 5, "1")])
-def test_fused_launches_equal_frame_by_frame(ctx, oracle_mod, monkeypatch, cells, k, decay, nframes, overlap):
-    """step(n) in one call (groups of up to 4 frames per launch, ring of counter images, composites on the
-    side stream) must leave exactly the state that n calls of step(1) leave -- which the tests above pin
-    to the oracle -- in every cell mode, across the warm-up / recording boundary (decay 0: splatting starts
-    there), across regroups, in x-wrap mode, and it must agree with the oracle itself."""
-    if cells != "auto":
-        monkeypatch.setenv("CLUMPY_CUDA_CELLS", cells)
-    monkeypatch.setenv("CLUMPY_CUDA_OVERLAP", overlap)
-    monkeypatch.setenv("CLUMPY_CUDA_REGROUP", "3")
+@pytest.mark.parametrize("cells", ["auto", "f16", "u32", "exact"])
+@pytest.mark.parametrize("k,decay,nframes,overlap,regroup", [(3, 0.97, 7, 1, 3), (1, 0.9, 5, -1, 3), (5, -0.95, 6, 1, 3), (3, 0.0, 5, 1, 3),
+                                                             (3, -0.97, 9, 1, -1), (1, 0.95, 8, 1, 8)])
+def test_fused_launches_equal_frame_by_frame(ctx, oracle_mod, cells, k, decay, nframes, overlap, regroup):
+    """step(n) in one call (groups of up to 8 frames per advect launch and per composite launch, three sets of
+    counter images, composites on the side stream) must leave exactly the state that n calls of step(1) leave
+    -- which the tests above pin to the oracle -- in every cell mode, across the warm-up / recording boundary
+    (decay 0: splatting starts there), across regroups, in x-wrap mode, and it must agree with the oracle."""
     w, h, n = 192, 128, 30000
     pot, _, _ = oracle_mod.generate_simplex(w, h, 1.0, 5.0, 4)
     vel, _, _ = oracle_mod.curl_2d(pot)
     pts = ((np.random.default_rng(8).random((n, 2)) * 1.06 - 0.03) * [w, h]).astype(np.float32)
-    one = ctx.advect(pts, vel, 45.0, k, decay, nframes)
-    monkeypatch.setenv("CLUMPY_CUDA_FUSE", "4")
-    many = ctx.advect(pts, vel, 45.0, k, decay, nframes)
+    one = ctx.advect(pts, vel, 45.0, k, decay, nframes, cells=cells, overlap=overlap, regroup=regroup, fuse=1)
+    many = ctx.advect(pts, vel, 45.0, k, decay, nframes, cells=cells, overlap=overlap, regroup=regroup)
     ref = oracle_mod.Advect(pts, vel, 45.0, k, decay, nframes)
     try:
         done = 0
-        for chunk in (1, 4, 3, 2, 4):  # 14 = 2 * 7 frames at most; groups 1 | 4 | 3 | 2 | 4
+        for chunk in (1, 4, 3, 8, 2, 4):  # groups are cut at regroups and at the warm-up / recording boundary
             chunk = min(chunk, 2 * nframes - done)
             if chunk == 0:
                 break
@@ -477,16 +474,14 @@ def test_fused_launches_equal_frame_by_frame(ctx, oracle_mod, monkeypatch, cells
 
 
 @pytest.mark.gpu
-def test_fused_launches_with_frame_copies_in_flight(ctx, oracle_mod, monkeypatch):
-    """The frame read-back ping-pong (frame_async) still sees every frame when the frames in between are
+def test_fused_launches_with_frame_copies_in_flight(ctx, oracle_mod):
+    """The frame read-back (frame_async) still sees every frame when the frames in between are
     advanced by fused launches."""
-    import clumpy_b200
-    monkeypatch.setenv("CLUMPY_CUDA_OVERLAP", "1")
     w, h, n, nframes = 256, 96, 40000, 6
     pot, _, _ = oracle_mod.generate_simplex(w, h, 1.0, 6.0, 2)
     vel, _, _ = oracle_mod.curl_2d(pot)
     pts = (np.random.default_rng(1).random((n, 2)) * [w, h]).astype(np.float32)
-    adv = ctx.advect(pts, vel, 50.0, 3, 0.96, nframes)
+    adv = ctx.advect(pts, vel, 50.0, 3, 0.96, nframes, overlap=1)
     ref = oracle_mod.Advect(pts, vel, 50.0, 3, 0.96, nframes)
     bufs = [np.empty((h, w), np.uint8) for _ in range(4)]
     want = []
@@ -504,3 +499,140 @@ def test_fused_launches_with_frame_copies_in_flight(ctx, oracle_mod, monkeypatch
     finally:
         adv.close()
         ref.close()
+
+
+# ---- round 2: group composite (composite_group.cu), recording, device-resident set-up ---------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,n,k,decay", [(128, 8, 3000, 3, 0.9), (127, 9, 3000, 3, 0.95), (130, 17, 5000, 1, 0.99), (4, 4, 200, 3, 0.5),
+                                           (1, 1, 50, 3, 0.9), (1000, 37, 60000, 3, 0.99), (257, 64, 40000, 3, -0.97), (3, 70, 500, 3, -0.9),
+                                           (1, 20, 300, 3, -0.9), (2, 20, 300, 3, -0.9)])
+def test_group_composite_shapes(ctx, oracle_mod, w, h, n, k, decay):
+    """Image sizes around the composite's 128 x 8 warp tiles and 4-pixel lanes (ragged right edge, byte path,
+    one-pixel images, x-wrap with images narrower than the sprite), half cells forced, groups of 1 .. 8 frames."""
+    rng = np.random.default_rng(w * 1000 + h)
+    vel = (rng.standard_normal((h, w, 2)) * 0.02).astype(np.float32)
+    pts = ((rng.random((n, 2)) * 1.1 - 0.05) * [w, h]).astype(np.float32)
+    nframes = 9
+    g = ctx.advect(pts, vel, 20.0, k, decay, nframes, cells="f16")
+    a = oracle_mod.Advect(pts, vel, 20.0, k, decay, nframes)
+    try:
+        for chunk in (1, 8, 5, 4):
+            g.step(chunk)
+            for _ in range(chunk):
+                a.step()
+            assert np.array_equal(a.points().view(np.uint32), g.points().view(np.uint32))
+            frac, worst = frame_agreement(g.image(), a.image())
+            assert frac >= FRAME_FRACTION and worst <= 1, (chunk, frac, worst)
+            if k == 1:
+                assert worst == 0
+    finally:
+        a.close()
+        g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cells,k", [("f16", 3), ("u32", 5), ("exact", 3), ("f16", 1)])
+def test_record_delivers_every_frame(ctx, oracle_mod, cells, k):
+    """clumpy_cuda_advect_record: every frame of fused groups lands in the caller's (pinned) buffer, identical
+    to stepping one frame at a time and reading the framebuffer."""
+    import torch
+    w, h, n, nframes = 200, 72, 25000 if cells != "exact" else 600, 7
+    pot, _, _ = oracle_mod.generate_simplex(w, h, 1.0, 6.0, 5)
+    vel, _, _ = oracle_mod.curl_2d(pot)
+    pts = (np.random.default_rng(3).random((n, 2)) * [w, h]).astype(np.float32)
+    rec = ctx.advect(pts, vel, 50.0, k, 0.96, nframes, cells=cells)
+    one = ctx.advect(pts, vel, 50.0, k, 0.96, nframes, cells=cells, fuse=1)
+    total = 2 * nframes
+    buf = torch.zeros((total, h, w), dtype=torch.uint8).pin_memory()
+    try:
+        rec.record(3, buf.data_ptr())
+        rec.record(total - 3, buf.data_ptr() + 3 * h * w)
+        rec.wait_frames()
+        for f in range(total):
+            one.step(1)
+            assert np.array_equal(buf[f].numpy(), one.image()), f
+        assert np.array_equal(rec.image(), one.image())
+    finally:
+        rec.close()
+        one.close()
+
+
+@pytest.mark.gpu
+def test_device_resident_setup_and_shards(ctx, oracle_mod):
+    """clumpy_cuda_advect_begin_ex with points, field and offsets already on the device (the simplex -> curl ->
+    advect chain without a host round trip), and with row shards selected on the device: the union of the
+    shards' trajectories is the unsharded run, bit for bit."""
+    import torch
+    import clumpy_b200
+    from clumpy_b200.multigpu import strip_edges
+    w, h, n, nframes = 320, 192, 50000, 5
+    d_pot = torch.empty((h, w), dtype=torch.float32, device="cuda")
+    d_vel = torch.empty((h, w, 2), dtype=torch.float32, device="cuda")
+    ctx.generate_simplex_dev(w, h, 0, h, 1.0, 5.0, 3, d_pot.data_ptr())
+    ctx.curl_2d_dev(d_pot.data_ptr(), w, h, None, d_vel.data_ptr())
+    ctx.sync()
+    vel = d_vel.cpu().numpy()
+    pts = ((np.random.default_rng(4).random((n, 2)) * 1.04 - 0.02) * [w, h]).astype(np.float32)
+    pts[:5] = [[np.nan, 3], [5, np.inf], [7, -np.inf], [9, -4], [11, 1e9]]
+    d_pts = torch.from_numpy(pts).cuda()
+    offs = clumpy_b200.age_offsets(nframes, n)
+    d_offs = torch.from_numpy(offs.astype(np.int32)).cuda()
+    ref = oracle_mod.Advect(pts, vel, 60.0, 3, 0.97, nframes)
+    dev = ctx.advect(d_pts.data_ptr(), d_vel.data_ptr(), 60.0, 3, 0.97, nframes, age_offset=d_offs.data_ptr(),
+                     npts=n, width=w, height=h)
+    rows = ctx.row_histogram(d_pts.data_ptr(), h, npts=n)
+    yy = np.clip(np.nan_to_num(pts[:, 1].astype(np.float64), nan=0.0, posinf=float(h), neginf=0.0), 0, h - 1).astype(np.int64)
+    assert np.array_equal(rows, np.bincount(yy, minlength=h))
+    edges = strip_edges(rows, 3)
+    shards = [ctx.advect(d_pts.data_ptr(), d_vel.data_ptr(), 60.0, 3, 0.97, nframes, npts=n, width=w, height=h,
+                         cells="count", shard_rows=(edges[r], edges[r + 1])) for r in range(3)]
+    try:
+        assert sum(s.n for s in shards) == n
+        for _ in range(2):
+            dev.step(nframes)
+            for s in shards:
+                s.step(nframes)
+            for _ in range(nframes):
+                ref.step()
+            want = ref.points()
+            assert np.array_equal(dev.points().view(np.uint32), want.view(np.uint32))
+            frac, worst = frame_agreement(dev.image(), ref.image())
+            assert frac >= FRAME_FRACTION and worst <= 1
+            got = np.empty_like(want)
+            seen = np.zeros(n, bool)
+            for s in shards:
+                pos, idx = s.points_indexed()
+                got[idx] = pos
+                seen[idx] = True
+            assert seen.all() and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    finally:
+        ref.close()
+        dev.close()
+        for s in shards:
+            s.close()
+
+
+@pytest.mark.gpu
+def test_age_offset_sentinel_never_resets(ctx, oracle_mod):
+    """Caller-supplied offsets >= nframes mean "never resets" (the reference's own sentinel, advect_points.cc:150)
+    instead of being wrapped into 16 bits."""
+    w, h, n, nframes = 96, 64, 4000, 6
+    rng = np.random.default_rng(12)
+    vel = np.full((h, w, 2), 0.01, np.float32)
+    pts = (rng.random((n, 2)) * [w, h]).astype(np.float32)
+    offs = rng.integers(0, nframes, n).astype(np.uint32)
+    offs[::3] = nframes          # never
+    offs[1::7] = 65536 + 2       # would alias phase 2 if truncated to 16 bits
+    g = ctx.advect(pts, vel, 30.0, 1, 0.9, nframes, age_offset=offs)
+    g.step(2 * nframes)
+    got = g.points()
+    g.close()
+    want = pts.copy()
+    step = np.float32(30.0) * np.float32(0.01)
+    for s in range(2 * nframes):
+        inside = (want[:, 0] >= 0) & (want[:, 0] < w) & (want[:, 1] >= 0) & (want[:, 1] < h)  # outside: velocity 0
+        want[inside] = want[inside] + step
+        reset = offs == (s % nframes)
+        want[reset] = pts[reset]
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

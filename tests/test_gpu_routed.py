@@ -17,20 +17,30 @@ pytestmark = pytest.mark.gpu
 
 
 class RanksOnOneGpu:
-    def __init__(self, world, pts, vel, step, k, decay, nframes, monkeypatch, overlap, shard="home_rows"):
+    def __init__(self, world, pts, vel, step, k, decay, nframes, overlap, shard="home_rows", on_device=False):
         import clumpy_b200
-        from clumpy_b200.multigpu import shard_indices
-        monkeypatch.setenv("CLUMPY_CUDA_CELLS", "f16" if k <= 3 else "u32")
-        monkeypatch.setenv("CLUMPY_CUDA_OVERLAP", "1" if overlap else "0")
-        monkeypatch.delenv("CLUMPY_CUDA_CELL_ROWS_MULTIPLE", raising=False)
+        from clumpy_b200.multigpu import shard_indices, strip_edges
         self.world, self.n, self.h, self.w = world, len(pts), vel.shape[0], vel.shape[1]
-        offsets = clumpy_b200.age_offsets(nframes, len(pts))
         self.ctxs = [clumpy_b200.Context(0) for _ in range(world)]
-        self.idx = [shard_indices(pts, self.h, world, r, shard) for r in range(world)]
-        self.advs = [c.advect(np.ascontiguousarray(pts[i]), vel, step, k, decay, nframes,
-                              age_offset=np.ascontiguousarray(offsets[i]))
-                     for c, i in zip(self.ctxs, self.idx)]
-        capacity = max(1, max(len(i) for i in self.idx))
+        opts = dict(cells="count", overlap=1 if overlap else -1)
+        if on_device:
+            # the shards are selected on the device from the whole list (desc.shard_row_lo / _hi), offsets drawn
+            # by the library: what bench.py and the CLI's multi-GPU driver do
+            rows = self.ctxs[0].row_histogram(pts, self.h)
+            edges = strip_edges(rows, world)
+            self.advs = [c.advect(pts, vel, step, k, decay, nframes, shard_rows=(edges[r], edges[r + 1]) if edges[r + 1] > edges[r] else (self.h, self.h + 1), **opts)
+                         for r, c in enumerate(self.ctxs)]
+            self.idx = None
+            sizes = [a.n for a in self.advs]
+            assert sizes == [int(rows[edges[r]:edges[r + 1]].sum()) for r in range(world)]
+        else:
+            offsets = clumpy_b200.age_offsets(nframes, len(pts))
+            self.idx = [shard_indices(pts, self.h, world, r, shard) for r in range(world)]
+            self.advs = [c.advect(np.ascontiguousarray(pts[i]), vel, step, k, decay, nframes,
+                                  age_offset=np.ascontiguousarray(offsets[i]), **opts)
+                         for c, i in zip(self.ctxs, self.idx)]
+            sizes = [len(i) for i in self.idx]
+        capacity = max(1, max(sizes))
         inboxes = [a.route_begin(r, world, capacity)[0] for r, a in enumerate(self.advs)]
         for a in self.advs:
             a.route_peers(inboxes)
@@ -50,8 +60,12 @@ class RanksOnOneGpu:
 
     def points(self):
         out = np.empty((self.n, 2), np.float32)
-        for a, i in zip(self.advs, self.idx):
-            out[i] = a.points()
+        for r, a in enumerate(self.advs):
+            if self.idx is None:
+                pos, idx = a.points_indexed()
+                out[idx] = pos
+            else:
+                out[self.idx[r]] = a.points()
         return out
 
     def close(self):
@@ -69,7 +83,7 @@ def _field(oracle_mod, w, h, seed=8):
     return vel
 
 
-@pytest.mark.parametrize("overlap,chunk", [(False, 1), (True, 1), (True, 4), (False, 3)])
+@pytest.mark.parametrize("overlap,chunk,on_device", [(False, 1, False), (True, 1, True), (True, 8, True), (False, 3, False), (True, 5, False)])
 @pytest.mark.parametrize("world,w,h,n,k,decay,nframes,step", [
     (2, 320, 200, 70001, 3, 0.98, 6, 35.0),
     (3, 256, 160, 30000, 1, 0.9, 5, 40.0),
@@ -78,11 +92,11 @@ def _field(oracle_mod, w, h, seed=8):
     (8, 300, 520, 90000, 3, 0.97, 5, 90.0),     # eight bands, fast field: many points change band
     (2, 128, 96, 5000, 3, 0.0, 3, 25.0),        # decay 0: warm-up frames do not splat at all
 ])
-def test_ranks_on_one_gpu_match_oracle(oracle_mod, monkeypatch, overlap, chunk, world, w, h, n, k, decay, nframes, step):
+def test_ranks_on_one_gpu_match_oracle(oracle_mod, overlap, chunk, on_device, world, w, h, n, k, decay, nframes, step):
     vel = _field(oracle_mod, w, h)
     # a cloud that also has points outside the image on every side
     pts = ((np.random.default_rng(21).random((n, 2)) * 1.04 - 0.02) * [w, h]).astype(np.float32)
-    run = RanksOnOneGpu(world, pts, vel, step, k, decay, nframes, monkeypatch, overlap)
+    run = RanksOnOneGpu(world, pts, vel, step, k, decay, nframes, overlap, on_device=on_device)
     ref = oracle_mod.Advect(pts, vel, step, k, decay, nframes)
     try:
         for s in range(0, 2 * nframes, chunk):
@@ -100,13 +114,13 @@ def test_ranks_on_one_gpu_match_oracle(oracle_mod, monkeypatch, overlap, chunk, 
         run.close()
 
 
-def test_index_sharding_routes_everything_through_inboxes(oracle_mod, monkeypatch):
+def test_index_sharding_routes_everything_through_inboxes(oracle_mod):
     """Contiguous index ranges: a rank's points are all over the image, so (world-1)/world of them
     travel through inboxes every frame."""
     w, h, n, k, nframes = 256, 192, 60000, 3, 4
     vel = _field(oracle_mod, w, h, seed=3)
     pts = (np.random.default_rng(5).random((n, 2)) * [w, h]).astype(np.float32)
-    run = RanksOnOneGpu(4, pts, vel, 50.0, k, 0.96, nframes, monkeypatch, True, shard="index")
+    run = RanksOnOneGpu(4, pts, vel, 50.0, k, 0.96, nframes, True, shard="index")
     ref = oracle_mod.Advect(pts, vel, 50.0, k, 0.96, nframes)
     try:
         for s in range(2 * nframes):
@@ -120,7 +134,7 @@ def test_index_sharding_routes_everything_through_inboxes(oracle_mod, monkeypatc
         run.close()
 
 
-def test_all_points_in_one_band_and_an_empty_rank(oracle_mod, monkeypatch):
+def test_all_points_in_one_band_and_an_empty_rank(oracle_mod):
     """Every point starts in the top rows: home-row sharding still balances the shards (strip edges are
     row quantiles), bands 1.. receive nothing at first, and a rank whose shard is empty still takes
     part in the fence."""
@@ -129,7 +143,7 @@ def test_all_points_in_one_band_and_an_empty_rank(oracle_mod, monkeypatch):
     rng = np.random.default_rng(9)
     pts = np.stack([rng.random(20000) * w, rng.random(20000) * 12.0], axis=1).astype(np.float32)
     for world, cloud in ((4, pts), (4, pts[:2])):  # 2 points on 4 ranks: two shards are empty
-        run = RanksOnOneGpu(world, cloud, vel, 45.0, 3, 0.95, nframes, monkeypatch, False)
+        run = RanksOnOneGpu(world, cloud, vel, 45.0, 3, 0.95, nframes, False, on_device=len(cloud) > 2)
         ref = oracle_mod.Advect(cloud, vel, 45.0, 3, 0.95, nframes)
         try:
             for s in range(2 * nframes):
@@ -145,14 +159,21 @@ def test_all_points_in_one_band_and_an_empty_rank(oracle_mod, monkeypatch):
 
 def test_dead_peer_times_out_instead_of_hanging(oracle_mod, monkeypatch):
     """A rank whose peer never publishes its epoch must not hang the GPU: the drain gives up after its
-    bounded wait and the time-out is reported."""
+    bounded wait (CLUMPY_ROUTE_TIMEOUT_MS), and the time-out is STICKY: every later call on the run fails with
+    CLUMPY_ERR_STATE instead of handing out incomplete frames."""
+    import clumpy_b200
+    monkeypatch.setenv("CLUMPY_ROUTE_TIMEOUT_MS", "300")
     w, h = 128, 96
     vel = _field(oracle_mod, w, h)
     pts = (np.random.default_rng(2).random((4000, 2)) * [w, h]).astype(np.float32)
-    run = RanksOnOneGpu(2, pts, vel, 20.0, 3, 0.9, 3, monkeypatch, False)
+    run = RanksOnOneGpu(2, pts, vel, 20.0, 3, 0.9, 3, False)
     try:
         run.advs[0].route_steps(1)      # rank 1 never runs this frame
         assert run.advs[0].route_errors() >= 1
+        for call in (lambda: run.advs[0].route_steps(1), lambda: run.advs[0].image()):
+            with pytest.raises(clumpy_b200.ClumpyCudaError) as e:
+                call()
+            assert e.value.code == clumpy_b200.ERR_STATE and "timed out" in str(e.value)
     finally:
         for a in run.advs:
             a.close()

@@ -13,6 +13,16 @@ import numpy as np
 import pytest
 
 
+@pytest.mark.parametrize("nframes", [1, 2, 7, 240, 1000, 65536, 1000003, 1500000000, 2**31 - 1, 2**30 + 7])
+def test_age_offsets_equal_the_standard_library(oracle_mod, nframes):
+    """The restated distribution (Lemire multiply-shift with rejection) against <random> itself, including
+    ranges where a large share of the draws is rejected (every rejection shifts all later draws)."""
+    if not oracle_mod.have_ref():
+        pytest.skip("oracle/_ref was not built here")
+    n = 400000
+    assert np.array_equal(oracle_mod.age_offsets(nframes, n), oracle_mod.ref_std_age_offsets(nframes, n))
+
+
 def test_perm_and_age_offsets_known_answers(oracle_mod, golden):
     m = golden["meta"]
     assert oracle_mod.simplex_perm(0)[:8].tolist() == m["perm_seed0_first8"]

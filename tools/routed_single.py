@@ -29,15 +29,14 @@ pts = synth_points(n, w, h)
 if os.environ.get("CLUMPY_ROUTE_LOOPBACK") != "1":  # (in loopback mode RoutedAdvect takes its rank's shard itself)
     pts = pts[: n // shard] if (len(sys.argv) > 3 and sys.argv[3] == "index") else pts[pts[:, 1] < h / shard]
 if os.environ.get("ROUTED_SINGLE_PLAIN") == "1":  # the single-GPU kernels on the same subset, for comparison
-    os.environ["CLUMPY_CUDA_CELLS"] = "f16"; os.environ["CLUMPY_CUDA_OVERLAP"] = "0"
-    adv = ctx.advect(pts, vel, cfg["step_size"], cfg["kernel_size"], cfg["decay"], cfg["nframes"])
+    adv = ctx.advect(pts, vel, cfg["step_size"], cfg["kernel_size"], cfg["decay"], cfg["nframes"], cells="f16", overlap=-1)
     adv.step(80); torch.cuda.synchronize()
-    print(f"plain advect, {len(pts)} points: advect/composite/clear ms: {adv.profile(50)}")
+    print(f"plain advect, {len(pts)} points: advect / composite ms per launch, frames per launch: {adv.profile_stages(12, serial=True)}")
     adv.close(); ctx.close(); dist.destroy_process_group(); sys.exit(0)
 run = RoutedAdvect(ctx, pts, vel, cfg["step_size"], cfg["kernel_size"], cfg["decay"], cfg["nframes"], dist, dev)
 run.step(80); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(stream); run.step(steps); e1.record(stream); torch.cuda.synchronize()
 print(f"routed single rank, {len(pts)} points on {w}x{h}: {e0.elapsed_time(e1)/steps:.4f} ms/frame; "
-      f"route/drain/composite ms: {run.adv.route_profile(20)}")
+      f"route / drain / composite ms per group, frames per group: {run.adv.route_profile(12)}")
 run.close(); ctx.close(); dist.destroy_process_group()
