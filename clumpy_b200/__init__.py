@@ -45,6 +45,9 @@ SIGNATURES = {
     "clumpy_cuda_generate_simplex_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                                    C.c_uint32, C.c_double, C.c_double, C.c_int64,
                                                    C.c_void_p, _f32p, _f32p]),
+    "clumpy_cuda_generate_simplex_octaves_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                           C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                                                           C.c_void_p, _f32p, _f32p]),
     "clumpy_cuda_curl_2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
                                       _f32p, _f32p]),
     "clumpy_cuda_curl_2d_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
@@ -296,6 +299,16 @@ class Context:
         lo, hi = C.c_float(), C.c_float()
         _check(lib().clumpy_cuda_generate_simplex_dev(
             self._h, width, height, row0, nrows, amplitude, frequency, int(seed), _vp(out_dev),
+            C.byref(lo) if want_range else None, C.byref(hi) if want_range else None))
+        return (lo.value, hi.value) if want_range else None
+
+    def generate_simplex_octaves_dev(self, width, height, row0, nrows, amplitudes, frequencies, seeds, out_dev, want_range=False):
+        """Rows [row0, row0 + nrows) of the FP32 sum of the octaves (amplitude, frequency, seed), in that order."""
+        n = len(amplitudes)
+        amps, freqs, sds = (C.c_double * n)(*amplitudes), (C.c_double * n)(*frequencies), (C.c_int64 * n)(*[int(s) for s in seeds])
+        lo, hi = C.c_float(), C.c_float()
+        _check(lib().clumpy_cuda_generate_simplex_octaves_dev(
+            self._h, width, height, row0, nrows, n, amps, freqs, sds, _vp(out_dev),
             C.byref(lo) if want_range else None, C.byref(hi) if want_range else None))
         return (lo.value, hi.value) if want_range else None
 

@@ -567,10 +567,16 @@ CLUMPY_API int clumpy_cuda_row_histogram(clumpy_cuda_ctx* ctx, const float* pts,
 template <bool WRAP, int MODE, typename OffT>
 static void launch_advect_t(clumpy_advect* a, uint32_t phase, int nf, const HistRing& ring) {
     const uint32_t grid = ceil_div(a->npts, ADVECT_THREADS * ADVECT_PTS);
-    const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch, a->keep_pos ? 1 : 0};
-    advect_fused_kernel<WRAP, MODE, OffT><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
-        a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase,
-        a->nframes, nf, g, ring);
+    const int hints = env_int("CLUMPY_CUDA_HINTS", 0), minb = env_int("CLUMPY_CUDA_ADVECT_MINB", 1); // (A/B switches)
+    const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch, a->keep_pos ? 1 : 0, hints};
+    if (minb == 8)
+        advect_fused_kernel<WRAP, MODE, OffT, 8><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
+            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase,
+            a->nframes, nf, g, ring);
+    else
+        advect_fused_kernel<WRAP, MODE, OffT, 1><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
+            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase,
+            a->nframes, nf, g, ring);
 }
 
 template <bool WRAP, int MODE>
@@ -655,7 +661,7 @@ static int advect_group(clumpy_advect* a, uint32_t nf, RecordSink* sink = nullpt
     const cudaStream_t main_stream = ctx->stream;
     const cudaStream_t side = overlap ? ctx->aux_stream : main_stream;
     const bool group_path = a->cell_mode == CELL_F16;
-    HistRing ring = {};
+    HistRing ring = {a->hist, a->hist_stride / sizeof(uint32_t), 0, a->nhist};
     const int set = (int)(a->group_index % NSETS);
     if (splat) {
         if (group_path) {
@@ -665,15 +671,15 @@ static int advect_group(clumpy_advect* a, uint32_t nf, RecordSink* sink = nullpt
                 CK(cudaStreamWaitEvent(main_stream, a->set_composited[z], 0));
                 a->set_pending[z] = false;
             }
-            for (uint32_t f = 0; f < nf; ++f) ring.image[f] = a->hist_buf[set * a->fuse + (int)f];
+            ring.first = set * a->fuse;
         } else {
+            ring.first = a->cellbuf;
             for (uint32_t f = 0; f < nf; ++f) { // these images were last used a ring ago: wait for their clears
                 const int b = (a->cellbuf + (int)f) % a->nhist;
                 if (a->clear_pending[b]) {
                     CK(cudaStreamWaitEvent(main_stream, a->cleared[b], 0));
                     a->clear_pending[b] = false;
                 }
-                ring.image[f] = a->hist_buf[b];
             }
         }
     }
@@ -696,7 +702,7 @@ static int advect_group(clumpy_advect* a, uint32_t nf, RecordSink* sink = nullpt
             ca.nf = (int)nf;
             ca.img_in = a->imgs[a->cur];
             for (uint32_t f = 0; f < nf; ++f) {
-                ca.cells[f] = ring.image[f];
+                ca.cells[f] = ring.image((int)f);
                 ca.frame_out[f] = slot[f] >= 0 ? a->imgs[slot[f]] : nullptr;
             }
             const int prev = (set + NSETS - 1) % NSETS;
@@ -852,8 +858,7 @@ CLUMPY_API int clumpy_cuda_advect_count(clumpy_advect* adv) {
     }
     for (int b = 0; b < LEGACY_RING; ++b)
         if (adv->clear_pending[b]) { CK(cudaStreamWaitEvent(ctx->stream, adv->cleared[b], 0)); adv->clear_pending[b] = false; }
-    HistRing ring = {};
-    ring.image[0] = adv->hist_buf[0];
+    const HistRing ring = {adv->hist, adv->hist_stride / sizeof(uint32_t), 0, adv->nhist};
     rc = launch_advect(adv, adv->simframe % adv->nframes, splat, 1, ring);
     if (rc) return rc;
     adv->count_open = true;
@@ -957,7 +962,7 @@ static uint32_t* route_band(const clumpy_advect* adv, int set, int f) {
 template <bool WRAP, bool SPLAT, typename OffT>
 static void launch_route_t(clumpy_advect* a, const RouteDev& rd) {
     const uint32_t grid = ceil_div(a->npts, ROUTE_BLOCK); // CTA c owns region c of its segments
-    const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch, a->keep_pos ? 1 : 0};
+    const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch, a->keep_pos ? 1 : 0, 0};
     if (a->route.minb == 8)
         advect_route_kernel<WRAP, SPLAT, OffT, 8><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
             a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);

@@ -35,6 +35,10 @@ __device__ __forceinline__ void cell_add_f16(uint32_t* __restrict__ words, long 
     const uint32_t one = (cell & 1) ? 0x3C000000u : 0x00003C00u;
     asm volatile("red.global.add.noftz.f16x2 [%0], %1;" :: "l"(words + (cell >> 1)), "r"(one) : "memory");
 }
+__device__ __forceinline__ void cell_add_f16(uint32_t* __restrict__ words, long long cell, uint64_t pol) {
+    const uint32_t one = (cell & 1) ? 0x3C000000u : 0x00003C00u;
+    asm volatile("red.global.add.L2::cache_hint.noftz.f16x2 [%0], %1, %2;" :: "l"(words + (cell >> 1)), "r"(one), "l"(pol) : "memory");
+}
 
 // Counts a point whose truncated position is (cx, cy) (splat_points.cc:143-144) into `hist`.
 // Half cells in x-wrap mode: the group composite (composite_group.cu) reads its halo columns as they are, so a
@@ -42,7 +46,7 @@ __device__ __forceinline__ void cell_add_f16(uint32_t* __restrict__ words, long 
 // side -- the cell its wrapped taps would be read from (splat_points.cc:149-151).
 template <bool WRAP, int MODE>
 __device__ __forceinline__ void count_point(uint32_t* __restrict__ hist, int32_t cx, int32_t cy, const GeomDev& g,
-                                            uint32_t slot) {
+                                            uint32_t slot, uint64_t red_pol) {
     const long long at = hist_index<WRAP>(cx, cy, g);
     if (at < 0) return;
     if (MODE == CELL_X64) {
@@ -51,7 +55,7 @@ __device__ __forceinline__ void count_point(uint32_t* __restrict__ hist, int32_t
     } else if (MODE == CELL_U32) {
         atomicAdd(hist + at, 1u);
     } else if (MODE == CELL_F16) {
-        cell_add_f16(hist, at);
+        cell_add_f16(hist, at, red_pol);
         if (WRAP && g.halo > 0) {
             int32_t m = cx % g.width;
             if (m < 0) m += g.width;
@@ -70,18 +74,23 @@ __device__ __forceinline__ void count_point(uint32_t* __restrict__ hist, int32_t
 // A CTA owns ADVECT_THREADS * ADVECT_PTS consecutive points; thread t takes t, t + 256, t + 512, ... so every
 // warp-wide access covers 32 CONSECUTIVE points: position / offset traffic is perfectly coalesced and, the
 // points being stored in tile order, a warp's gather touches only a few lines.
-struct HistRing {
-    uint32_t* image[ADVECT_MAX_FUSE]; // counter image of frame f of the group
+struct HistRing { // frame f of the group counts into image (first + f) % count
+    uint32_t* base;
+    size_t stride_words;
+    int first, count;
+    __host__ __device__ uint32_t* image(int f) const { return base + (size_t)((first + f) % count) * stride_words; }
 };
 
-template <bool WRAP, int MODE, typename OffT>
-__global__ void __launch_bounds__(ADVECT_THREADS)
+template <bool WRAP, int MODE, typename OffT, int MINB>
+__global__ void __launch_bounds__(ADVECT_THREADS, MINB)
 advect_fused_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                     const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
                     uint32_t width, uint32_t height, float step, uint32_t phase0, uint32_t nframes, int nf,
                     GeomDev g, HistRing ring) {
     const uint32_t base = blockIdx.x * (ADVECT_THREADS * ADVECT_PTS) + threadIdx.x;
     const uint64_t pol = g.keep_pos == 0 ? make_stream_policy() : make_normal_policy();
+    const uint64_t vel_pol = (g.hints & 1) ? make_keep_policy() : make_normal_policy();
+    const uint64_t red_pol = (g.hints & 2) ? make_stream_policy() : make_normal_policy();
     float2 p[ADVECT_PTS];
     uint32_t off[ADVECT_PTS];
     bool live[ADVECT_PTS];
@@ -105,7 +114,7 @@ advect_fused_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
             const uint32_t y = f2u32_x86(p[k].y);
             if (WRAP) x = (width + (x % width)) % width;
             v[k] = make_float2(0.f, 0.f);
-            if (live[k] && x < width && y < height) v[k] = __ldg(vel + ((size_t)y * width + x));
+            if (live[k] && x < width && y < height) v[k] = ld_gather_f2(vel + ((size_t)y * width + x), vel_pol);
         }
 #pragma unroll
         for (int k = 0; k < ADVECT_PTS; ++k) {
@@ -115,10 +124,10 @@ advect_fused_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
         }
         phase = phase + 1u == nframes ? 0u : phase + 1u;
         if (MODE != CELL_NONE) {
-            uint32_t* hist = ring.image[f];
+            uint32_t* hist = ring.image(f);
 #pragma unroll
             for (int k = 0; k < ADVECT_PTS; ++k) // splat_points.cc:143-144: centre texel by (int32_t) truncation
-                if (live[k]) count_point<WRAP, MODE>(hist, f2i32_x86(p[k].x), f2i32_x86(p[k].y), g, base + k * ADVECT_THREADS);
+                if (live[k]) count_point<WRAP, MODE>(hist, f2i32_x86(p[k].x), f2i32_x86(p[k].y), g, base + k * ADVECT_THREADS, red_pol);
         }
     }
 #pragma unroll

@@ -33,12 +33,14 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 namespace clumpy {
 
-constexpr int GC_THREADS = 512;   // 16 warps; one CTA per SM (the k = 3 table takes the shared memory)
+constexpr int GC_THREADS = 512;   // default: 16 warps; one CTA per SM (the k = 3 table takes the shared memory)
 constexpr int GC_ROWS = 8;        // image rows per warp tile
 constexpr int GC_TILE_W = 128;    // pixels per warp tile row: 32 lanes x 4 pixels
 constexpr int GC_ROW_BYTES = 260; // table row stride
@@ -134,8 +136,10 @@ __device__ __forceinline__ uint32_t lookup4(const uint8_t* __restrict__ tab, uin
 
 struct CellRow { uint32_t w0, w1, e; }; // cells (x0-1, x0), (x0+1, x0+2), (x0+3, x0+4) as half2 bit patterns
 
-template <int K>
-__global__ void __launch_bounds__(GC_THREADS, 2) // 64 registers: half the file stays free for the advect kernel
+// THREADS: 512 by default (64 registers each: half the register file stays free for the advect kernel that
+// shares the SM); 256 (128 registers, no spills) and 1024 exist for A/B runs (CLUMPY_CUDA_COMPOSITE_THREADS).
+template <int K, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2)
 composite_group_kernel(GroupCompositeArgs a, const uint8_t* __restrict__ table_g, uint32_t table_bytes) {
     extern __shared__ __align__(128) uint8_t tab[];
     __shared__ __align__(8) unsigned long long bar;
@@ -159,11 +163,13 @@ composite_group_kernel(GroupCompositeArgs a, const uint8_t* __restrict__ table_g
 
     // 2. meanwhile: zero the counter images of the group before this one (they were read by the launch
     //    before this one on the same stream and are counted into again two groups on)
+    const uint64_t zero_pol = (a.hints & 8) ? make_stream_policy() : make_normal_policy();
+    const uint64_t cell_pol = (a.hints & 4) ? make_stream_policy() : make_normal_policy();
     for (int z = 0; z < a.nzero; ++z) {
         uint4* p = a.zero[z];
         const uint32_t n16 = a.zero_n16[z];
-        for (uint32_t i = blockIdx.x * GC_THREADS + threadIdx.x; i < n16; i += gridDim.x * GC_THREADS)
-            p[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < n16; i += gridDim.x * THREADS)
+            st_hint_u4(p + i, make_uint4(0u, 0u, 0u, 0u), zero_pol);
     }
 
     // 3. wait for the table
@@ -198,7 +204,7 @@ composite_group_kernel(GroupCompositeArgs a, const uint8_t* __restrict__ table_g
     const __half2 mul1 = __float2half2_rn(a.depth[1] + 1.0f), mul2 = __float2half2_rn(a.depth[2] + 1.0f);
     const __half2 bias = __float2half2_rn(1024.0f); // 1024 + i has the bit pattern 0x6400 | i for i < 1024
 
-    const int warp = blockIdx.x * (GC_THREADS / 32) + (threadIdx.x >> 5), nwarp = gridDim.x * (GC_THREADS / 32);
+    const int warp = blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5), nwarp = gridDim.x * (THREADS / 32);
     for (int t = warp; t < a.ntiles; t += nwarp) {
         const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
         const int y0 = ty * GC_ROWS, x0 = tx * GC_TILE_W + 4 * lane;
@@ -224,7 +230,7 @@ composite_group_kernel(GroupCompositeArgs a, const uint8_t* __restrict__ table_g
             if (K == 1) {
 #pragma unroll
                 for (int r = 0; r < GC_ROWS; ++r) {
-                    const uint2 v = __ldcg(reinterpret_cast<const uint2*>(base + (size_t)r * a.pitch));
+                    const uint2 v = ld_stream_u2(reinterpret_cast<const uint2*>(base + (size_t)r * a.pitch), cell_pol);
                     const __half2 u01 = __hadd2(__hmin2(as_h2(v.x), lim0), bias);
                     const __half2 u23 = __hadd2(__hmin2(as_h2(v.y), lim0), bias);
                     px[r] = lookup4(tab, px[r], as_u32(u01), as_u32(u23));
@@ -234,12 +240,12 @@ composite_group_kernel(GroupCompositeArgs a, const uint8_t* __restrict__ table_g
 #pragma unroll
                 for (int r = 0; r < GC_ROWS + 2; ++r) {
                     const __half* p = base + (size_t)r * a.pitch;
-                    const uint2 v = __ldcg(reinterpret_cast<const uint2*>(p));
+                    const uint2 v = ld_stream_u2(reinterpret_cast<const uint2*>(p), cell_pol);
                     row[r].w0 = v.x;
                     row[r].w1 = v.y;
                     // the next lane's first word = cells (x0+3, x0+4); lane 31 reads it from memory
                     uint32_t e = 0u;
-                    if (lane == 31) e = __ldcg(reinterpret_cast<const uint32_t*>(p + 4));
+                    if (lane == 31) e = ld_stream_u1(reinterpret_cast<const uint32_t*>(p + 4), cell_pol);
                     const uint32_t up = __shfl_down_sync(0xFFFFFFFFu, v.x, 1);
                     row[r].e = lane == 31 ? e : up;
                 }
@@ -288,16 +294,22 @@ int launch_composite_group(clumpy_cuda_ctx* ctx, cudaStream_t stream, const Grou
     bool vec = a.img_pitch % 4 == 0 && (uintptr_t)a.img_in % 4 == 0;
     for (int f = 0; f < a.nf; ++f) vec = vec && (uintptr_t)a.frame_out[f] % 4 == 0;
     a.vec_ok = vec ? 1 : 0;
-    int grid = std::min(ctx->sm_count, (int)ceil_div((uint32_t)a.ntiles, GC_THREADS / 32));
+    const int hints_env = [] { const char* v = getenv("CLUMPY_CUDA_HINTS"); return v ? atoi(v) : 0; }();
+    a.hints = hints_env;
+    const int threads_env = [] { const char* v = getenv("CLUMPY_CUDA_COMPOSITE_THREADS"); return v ? atoi(v) : 0; }();
+    const int threads = threads_env == 256 || threads_env == 1024 ? threads_env : GC_THREADS;
+    int grid = std::min(ctx->sm_count, (int)ceil_div((uint32_t)a.ntiles, (uint32_t)threads / 32));
     if (a.nzero > 0) grid = ctx->sm_count;
-    auto kern = t.kernel_size == 1 ? composite_group_kernel<1> : composite_group_kernel<3>;
-    static thread_local int attr_set_for = -1; // the opt-in is per device and function
-    if (attr_set_for != ctx->device) {
-        CK(cudaFuncSetAttribute(composite_group_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-        CK(cudaFuncSetAttribute(composite_group_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-        attr_set_for = ctx->device;
+    using Kern = void (*)(GroupCompositeArgs, const uint8_t*, uint32_t);
+    const Kern kern = t.kernel_size == 1 ? (threads == 256 ? composite_group_kernel<1, 256> : threads == 1024 ? composite_group_kernel<1, 1024> : composite_group_kernel<1, 512>)
+                                         : (threads == 256 ? composite_group_kernel<3, 256> : threads == 1024 ? composite_group_kernel<3, 1024> : composite_group_kernel<3, 512>);
+    // the opt-in to more than 48 KB of dynamic shared memory is per device and function
+    static thread_local std::vector<std::pair<int, Kern>> opted;
+    if (std::find(opted.begin(), opted.end(), std::make_pair(ctx->device, kern)) == opted.end()) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        opted.emplace_back(ctx->device, kern);
     }
-    kern<<<grid, GC_THREADS, t.bytes, stream>>>(a, t.d_table, (uint32_t)t.bytes);
+    kern<<<grid, threads, t.bytes, stream>>>(a, t.d_table, (uint32_t)t.bytes);
     CK_LAUNCH(ctx);
     return CLUMPY_OK;
 }

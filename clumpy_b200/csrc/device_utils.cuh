@@ -68,6 +68,8 @@ __device__ __forceinline__ void block_minmax_commit(float lo, bool has_lo, float
 struct GeomDev {
     int width, height, halo, pitch;
     int keep_pos; // advect kernels: 1 = positions keep the normal L2 policy (default 0: evict-first stream)
+    int hints;    // L2 eviction priorities (CLUMPY_CUDA_HINTS, A/B): bit 0 = velocity gathers evict-last,
+                  // bit 1 = counter reductions evict-first
 };
 
 // Index of the counter for a point whose truncated position is (cx, cy), or -1 when none of its
@@ -107,6 +109,11 @@ __device__ __forceinline__ uint64_t make_normal_policy() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
     return pol;
+}
+__device__ __forceinline__ float2 ld_gather_f2(const float2* p, uint64_t pol) { // read-only data, through L1
+    float2 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(p), "l"(pol));
+    return v;
 }
 __device__ __forceinline__ uint32_t ld_hint_u32(const uint32_t* p, uint64_t pol) {
     uint32_t v;

@@ -125,6 +125,58 @@ simplex_kernel(const PermArg perm_arg, uint32_t width, uint32_t row0, uint64_t n
     block_minmax_commit(lo, any, hi, any, minmax);
 }
 
+// Several octaves in one pass (README.md:28-36, extras/test.py:18-21: the reference runs generate_simplex once
+// per octave and sums the .npy files with numpy, i.e. in FP32, left to right).  Each octave's value is computed
+// exactly as simplex_kernel computes it (same FP32 coordinate product, same FP64 placement, same scale), and the
+// octaves are added in FP32 in the order given, so the field equals the sum of the single-octave fields bit for
+// bit -- without writing and re-reading one 1 GB image per octave at the C3 size.
+constexpr int SIMPLEX_MAX_OCTAVES = 8;
+struct OctavePerms { uint8_t p[SIMPLEX_MAX_OCTAVES][256]; };
+struct OctaveArgs { int n; float step[SIMPLEX_MAX_OCTAVES]; float scale[SIMPLEX_MAX_OCTAVES]; };
+
+__global__ void __launch_bounds__(SIMPLEX_THREADS)
+simplex_octaves_kernel(const OctavePerms perms_arg, const OctaveArgs oa, uint32_t width, uint32_t row0, uint64_t npix,
+                       float* __restrict__ out, uint32_t* __restrict__ minmax, int vec_ok) {
+    __shared__ uint8_t perm[SIMPLEX_MAX_OCTAVES][256];
+    for (int o = 0; o < oa.n; ++o) perm[o][threadIdx.x] = perms_arg.p[o][threadIdx.x]; // blockDim.x == 256
+    __syncthreads();
+
+    float lo = 0.f, hi = 0.f;
+    bool any = false;
+    const uint64_t chunk = (uint64_t)SIMPLEX_THREADS * SIMPLEX_PX;
+    for (uint64_t base = (uint64_t)blockIdx.x * chunk + (uint64_t)threadIdx.x * SIMPLEX_PX;
+         base < npix; base += (uint64_t)gridDim.x * chunk) {
+        uint32_t row = (uint32_t)(base / width);
+        uint32_t col = (uint32_t)(base - (uint64_t)row * width);
+        float vals[SIMPLEX_PX];
+        const int n = (npix - base < SIMPLEX_PX) ? (int)(npix - base) : SIMPLEX_PX;
+#pragma unroll
+        for (int k = 0; k < SIMPLEX_PX; ++k) {
+            if (k < n) {
+                float total = 0.f;
+                for (int o = 0; o < oa.n; ++o) {
+                    const float uf = __fmul_rn(oa.step[o], (float)col);
+                    const float vf = __fmul_rn(oa.step[o], (float)(row0 + row));
+                    const float s = simplex2(perm[o], uf, vf) * oa.scale[o];
+                    total = o == 0 ? s : __fadd_rn(total, s);
+                }
+                vals[k] = total;
+                if (!any) { lo = hi = total; any = true; }
+                else { lo = (total < lo) ? total : lo; hi = (hi < total) ? total : hi; }
+                if (++col == width) { col = 0; ++row; }
+            }
+        }
+        if (vec_ok && n == SIMPLEX_PX) {
+            *reinterpret_cast<float4*>(out + base) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < SIMPLEX_PX; ++k)
+                if (k < n) out[base + k] = vals[k];
+        }
+    }
+    block_minmax_commit(lo, any, hi, any, minmax);
+}
+
 static int run_simplex(clumpy_cuda_ctx* ctx, uint32_t width, uint32_t height, uint32_t row0,
                        uint32_t nrows, double amplitude, double frequency, int64_t seed,
                        float* d_out, float* minval, float* maxval) {
@@ -186,6 +238,42 @@ CLUMPY_API int clumpy_cuda_generate_simplex_dev(clumpy_cuda_ctx* ctx, uint32_t w
     CK(cudaSetDevice(ctx->device));
     return run_simplex(ctx, width, height, row0, nrows, amplitude, frequency, seed, out_dev, minval,
                        maxval);
+}
+
+CLUMPY_API int clumpy_cuda_generate_simplex_octaves_dev(clumpy_cuda_ctx* ctx, uint32_t width, uint32_t height,
+                                                        uint32_t row0, uint32_t nrows, uint32_t noctaves,
+                                                        const double* amplitudes, const double* frequencies,
+                                                        const int64_t* seeds, float* out_dev, float* minval, float* maxval) {
+    REQUIRE(ctx && amplitudes && frequencies && seeds, "null argument");
+    REQUIRE(width > 0 && height > 0, "image dimensions must be positive");
+    REQUIRE((uint64_t)row0 + nrows <= height, "row band exceeds the image");
+    REQUIRE(out_dev || nrows == 0, "out_dev is NULL");
+    REQUIRE(noctaves >= 1 && noctaves <= (uint32_t)SIMPLEX_MAX_OCTAVES, "1 .. 8 octaves");
+    CK(cudaSetDevice(ctx->device));
+    OctavePerms perms;
+    OctaveArgs oa;
+    oa.n = (int)noctaves;
+    for (uint32_t o = 0; o < noctaves; ++o) {
+        int16_t perm16[256];
+        clumpy_cuda_simplex_perm(seeds[o], perm16);
+        for (int i = 0; i < 256; ++i) perms.p[o][i] = (uint8_t)perm16[i];
+        // generate_simplex.cc:59-67 and :77, per octave
+        oa.step[o] = (width > height) ? (float)(frequencies[o] / height) : (float)(frequencies[o] / width);
+        oa.scale[o] = (float)(amplitudes[o] / 47.0);
+    }
+    const uint64_t npix = (uint64_t)nrows * width;
+    int rc = minmax_reset(ctx);
+    if (rc) return rc;
+    if (npix > 0) {
+        const uint64_t chunk = (uint64_t)SIMPLEX_THREADS * SIMPLEX_PX;
+        const uint64_t want = (npix + chunk - 1) / chunk, cap = (uint64_t)ctx->sm_count * 8 * 4;
+        const int vec_ok = ((uintptr_t)out_dev % 16 == 0) ? 1 : 0;
+        simplex_octaves_kernel<<<(uint32_t)(want < cap ? want : cap), SIMPLEX_THREADS, 0, ctx->stream>>>(
+            perms, oa, width, row0, npix, out_dev, ctx->d_minmax, vec_ok);
+        CK_LAUNCH(ctx);
+    }
+    if (minval || maxval) return minmax_fetch(ctx, minval, maxval);
+    return CLUMPY_OK;
 }
 
 CLUMPY_API int clumpy_cuda_generate_simplex(clumpy_cuda_ctx* ctx, uint32_t width, uint32_t height,

@@ -1,13 +1,12 @@
 // advect_points -- same command name, arguments, messages, frame naming and .npy output as the
-// reference (commands/advect_points.cc:39-183 there).  Argument parsing, input validation, the
-// mt19937 reset offsets and the file writes stay on the host; the 2*nframes simulation frames
+// reference (commands/advect_points.cc:39-183 there).  Argument parsing, input validation and the file writes
+// stay on the host here; the mt19937 reset offsets (:127-135) are drawn on a host thread inside the library
+// while it uploads (clumpy_cuda_age_offsets: the same values as <random>'s); the 2*nframes simulation frames
 // (Euler step, reset, u8 decay, splat) run in clumpy_cuda_advect_points, which hands back each
 // recorded framebuffer from pinned memory while the GPU simulates the next one.
 #include "clumpy_command.hh"
 #include "gpu.hh"
 #include "npy.hh"
-
-#include <random>
 
 using std::string;
 using std::vector;
@@ -89,31 +88,29 @@ bool AdvectPoints::exec(vector<string> args) {
         printf("Velocities have wrong data type.\n");
         return false;
     }
-    if (0 == (kernel_size % 2)) { // the reference reaches this inside splat_disks and exits 1
-        printf("Kernel size must be an odd integer.\n");
-        return false;
-    }
     const uint32_t npts = pts.shape[0], height = vel.shape[0], width = vel.shape[1];
-    if (nframes == 0) {
+    if (nframes == 0) { // (the reference divides by zero in its progress bar here)
         printf("\nGenerated %03d%s through %03u%s.\n", 0, suffix.c_str(), 0u - 1u, suffix.c_str());
         return true;
     }
-
-    vector<uint32_t> age_offset(npts);
-    {
-        std::mt19937 generator;
-        generator.seed(0);
-        std::uniform_int_distribution<> get_age_offset(0, nframes - 1);
-        for (uint32_t i = 0; i < npts; ++i) age_offset[i] = get_age_offset(generator);
+    if (0 == (kernel_size % 2)) {
+        // the reference reaches this inside splat_disks, in its first simulation frame, and exits 1
+        // (splat_points.cc:122-125): the first progress bar is already out by then
+        show_progress(0, 2 * nframes);
+        printf("Kernel size must be an odd integer.\n");
+        return false;
     }
 
     Gpu gpu;
     if (!gpu) return false;
     FrameSink sink{suffix, width, height, nframes};
-    show_progress(0, 2 * nframes);
+    // The reference redraws its bar once per simulation frame (advect_points.cc:140).  The warm-up half runs
+    // on the device in one go here (milliseconds), so its bars are printed up front; the recorded half's are
+    // printed as the frames arrive (write_frame): stdout is byte-identical to the reference's.
+    for (uint32_t s = 0; s < nframes; ++s) show_progress(s, 2 * nframes);
     const int rc = clumpy_cuda_advect_points(gpu.ctx, pts.data<float>(), npts, vel.data<float>(), width, height,
                                              step_size, kernel_size, decay, advect_wrapx ? 1 : 0, nframes,
-                                             age_offset.data(), write_frame, &sink);
+                                             /*age_offset=*/nullptr, write_frame, &sink);
     if (sink.failed) {
         printf("\nCould not write frame %03u%s\n", sink.written, suffix.c_str());
         return false;

@@ -57,17 +57,19 @@ bool SplatPoints::exec(vector<string> args) {
     const uint32_t npts = arr.shape[0];
     vector<uint8_t> dstimg((size_t)width * height);
     printf("Drawing %u points.\n", npts);
+    const bool fast_path = alpha == 1 && kernel_size == 1; // splat_points.cc:93-94
+    if (!fast_path && !disk) {
+        printf("Only disks are implemented right now.\n");
+        return false;
+    }
     Gpu gpu;
     if (!gpu) return false;
     int rc;
-    if (alpha == 1 && kernel_size == 1) {
+    if (fast_path) {
         rc = clumpy_cuda_splat_points(gpu.ctx, arr.data<float>(), npts, width, height, dstimg.data());
-    } else if (disk) {
+    } else {
         rc = clumpy_cuda_splat_disks(gpu.ctx, arr.data<float>(), npts, width, height, dstimg.data(), alpha,
                                      kernel_size, advect_wrapx ? 1 : 0);
-    } else {
-        printf("Only disks are implemented right now.\n");
-        return false;
     }
     if (!Gpu::report(rc)) return false;
     return npy::save_u8(args[5], dstimg.data(), {height, width});

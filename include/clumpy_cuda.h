@@ -93,6 +93,15 @@ int clumpy_cuda_generate_simplex_dev(clumpy_cuda_ctx* ctx, uint32_t width, uint3
                                      double frequency, int64_t seed, float* out_dev,
                                      float* minval, float* maxval);
 
+/* Several octaves in one pass: the sum, in FP32 and in the order given, of the fields generate_simplex produces
+ * for (amplitudes[o], frequencies[o], seeds[o]) -- what the reference's users compute by running the command once
+ * per octave and adding the files with numpy (README.md:28-36, extras/test.py:18-21).  Bit-identical to adding this
+ * library's single-octave outputs; 1 <= noctaves <= 8.  Row bands as above. */
+int clumpy_cuda_generate_simplex_octaves_dev(clumpy_cuda_ctx* ctx, uint32_t width, uint32_t height,
+                                             uint32_t row0, uint32_t nrows, uint32_t noctaves,
+                                             const double* amplitudes, const double* frequencies,
+                                             const int64_t* seeds, float* out_dev, float* minval, float* maxval);
+
 /* ---- curl_2d --------------------------------------------------------------------------- */
 
 /* Replaces the loop of commands/curl_2d.cc:57-71.  src_host (height, width) float32 ->

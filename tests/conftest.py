@@ -32,7 +32,15 @@ def golden():
         "splat": dict(np.load(os.path.join(GOLDEN, "splat_small.npz"))),
         "c1_pts": np.load(os.path.join(GOLDEN, "c1_pts.npy")),
         "next": dict(np.load(os.path.join(GOLDEN, "next_small.npz"))),
+        "c2_pts": np.load(os.path.join(GOLDEN, "c2_pts.npy")),
+        "c3_corner": np.load(os.path.join(GOLDEN, "c3_octaves_corner.npz"))["total"],
     }
+
+
+@pytest.fixture(scope="session")
+def c2_frames():
+    """Frames 0, 199 and 399 of README example6 from the reference CLI (4000 x 2000 u8 each)."""
+    return dict(np.load(os.path.join(GOLDEN, "c2_frames.npz")))
 
 
 @pytest.fixture(scope="session")

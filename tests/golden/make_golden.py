@@ -40,7 +40,8 @@ def main():
     out = run("curl_2d", "potential.npy", "velocity.npy")
     meta["c1_curl_stdout"] = out.strip().splitlines()
     run("bridson_points", "1000x500", "5", "0", "pts.npy")
-    run("advect_points", "pts.npy", "velocity.npy", "30", "1", "0.95", "240", "anim.npy")
+    out = run("advect_points", "pts.npy", "velocity.npy", "30", "1", "0.95", "240", "anim.npy")
+    meta["c1_advect_stdout_md5"] = hashlib.md5(out.encode()).hexdigest()  # 480 progress bars + the "Generated ..." line
     meta["c1_md5"] = {n: md5(os.path.join(tmp, n)) for n in ("potential.npy", "velocity.npy", "pts.npy")}
     meta["c1_frame_md5"] = [md5(os.path.join(tmp, f"{i:03}anim.npy")) for i in range(240)]
     meta["c1_frame_data_md5"] = [hashlib.md5(load(f"{i:03}anim.npy").tobytes()).hexdigest() for i in range(240)]
@@ -121,6 +122,86 @@ def main():
     meta["c2_md5"] = {"field.npy": md5(os.path.join(tmp, "field.npy")), "pts.npy": md5(os.path.join(tmp, "pts_c2.npy"))}
     meta["c2_field_data_md5"] = hashlib.md5(load("field.npy").tobytes()).hexdigest()
     meta["c2_pts_data_md5"] = hashlib.md5(load("pts_c2.npy").tobytes()).hexdigest()
+    # C2 advect (README.md:119-121, extras/example6.py:16-30): all 400 frames by hash (file and data), three of
+    # them -- 4000 x 2000, mostly black -- stored compressed so that the CUDA path's "exact order" regime (k = 5,
+    # sparse cloud: identical on all but a handful of pixels, never more than 1 LSB off) can be checked at size
+    run("advect_points", "pts_c2.npy", "field.npy", "2.5", "5", "0.99", "400", "phase.npy")
+    meta["c2_frame_md5"] = [md5(os.path.join(tmp, f"{i:03}phase.npy")) for i in range(400)]
+    meta["c2_frame_data_md5"] = [hashlib.md5(load(f"{i:03}phase.npy").tobytes()).hexdigest() for i in range(400)]
+    assert meta["c2_frame_md5"][0] == "0653b18c35d09cfb201d30f75290bdb7" and meta["c2_frame_md5"][399] == "293c59068e2acafb378d9980cc4350aa", \
+        "C2 frames differ from SURVEY.md 8(c)"
+    shutil.copy(os.path.join(tmp, "pts_c2.npy"), os.path.join(HERE, "c2_pts.npy"))
+    np.savez_compressed(os.path.join(HERE, "c2_frames.npz"), **{f"frame_{i:03}": load(f"{i:03}phase.npy") for i in (0, 199, 399)})
+    for i in range(400):
+        os.unlink(os.path.join(tmp, f"{i:03}phase.npy"))
+    # the argument-error messages of the four headline commands (advect_points.cc:65-68,84-104,
+    # splat_points.cc:45-48,58-61,64-100, generate_simplex.cc:44-47, curl_2d.cc:30-45), from the reference itself
+    import subprocess
+    def fails(*a):
+        p = subprocess.run([oracle.REF_CLI] + [str(x) for x in a], cwd=tmp, capture_output=True, text=True)
+        return {"args": [str(x) for x in a], "rc": p.returncode, "stdout": p.stdout.strip()}
+    np.save(os.path.join(tmp, "pts3.npy"), np.zeros((4, 3), np.float32))
+    np.save(os.path.join(tmp, "pts64.npy"), np.zeros((4, 2), np.float64))
+    np.save(os.path.join(tmp, "pts1d.npy"), np.zeros(8, np.float32))
+    np.save(os.path.join(tmp, "vel2d.npy"), np.zeros((8, 8), np.float32))
+    np.save(os.path.join(tmp, "vel64.npy"), np.zeros((8, 8, 2), np.float64))
+    np.save(os.path.join(tmp, "ok_pts.npy"), np.ones((4, 2), np.float32))
+    np.save(os.path.join(tmp, "ok_vel.npy"), np.zeros((8, 8, 2), np.float32))
+    np.save(os.path.join(tmp, "img3d.npy"), np.zeros((4, 4, 2), np.float32))
+    np.save(os.path.join(tmp, "img64.npy"), np.zeros((4, 4), np.float64))
+    meta["cli_errors"] = [
+        fails("advect_points", "a", "b"),
+        fails("advect_points", "pts3.npy", "ok_vel.npy", "1", "1", "0.9", "2", "x.npy"),
+        fails("advect_points", "pts64.npy", "ok_vel.npy", "1", "1", "0.9", "2", "x.npy"),
+        fails("advect_points", "ok_pts.npy", "vel2d.npy", "1", "1", "0.9", "2", "x.npy"),
+        fails("advect_points", "ok_pts.npy", "vel64.npy", "1", "1", "0.9", "2", "x.npy"),
+        fails("advect_points", "ok_pts.npy", "ok_vel.npy", "1", "4", "0.9", "2", "x.npy"),
+        fails("splat_points", "a"),
+        fails("splat_points", "ok_pts.npy", "8x8", "u8disk", "2", "1.0", "x.npy"),
+        fails("splat_points", "ok_pts.npy", "8x8", "fp32sphere", "3", "1.0", "x.npy"),
+        fails("splat_points", "ok_pts.npy", "8x8", "bogus", "3", "1.0", "x.npy"),
+        fails("splat_points", "pts1d.npy", "8x8", "u8disk", "3", "1.0", "x.npy"),
+        fails("splat_points", "pts3.npy", "8x8", "u8disk", "3", "1.0", "x.npy"),
+        fails("splat_points", "pts64.npy", "8x8", "u8disk", "3", "1.0", "x.npy"),
+        fails("generate_simplex", "8x8"),
+        fails("curl_2d", "a"),
+        fails("curl_2d", "img3d.npy", "x.npy"),
+        fails("curl_2d", "img64.npy", "x.npy"),
+    ]
+    # the printed ranges at the C4 / C3 field sizes and a few texels of each
+    out = run("generate_simplex", "8192x4096", "1.0", "8.0", "0", "pot_c4.npy")
+    meta["c4_simplex_stdout"] = out.strip()
+    meta["c4_curl_stdout"] = run("curl_2d", "pot_c4.npy", "vel_c4.npy").strip().splitlines()
+    os.unlink(os.path.join(tmp, "vel_c4.npy"))
+    out = run("generate_simplex", "16384x16384", "1.0", "8.0", "0", "pot_c3.npy")
+    meta["c3_simplex_stdout"] = out.strip()
+    meta["c3_curl_stdout"] = run("curl_2d", "pot_c3.npy", "vel_c3.npy").strip().splitlines()
+    pot3 = np.load(os.path.join(tmp, "pot_c3.npy"), mmap_mode="r")
+    vel3 = np.load(os.path.join(tmp, "vel_c3.npy"), mmap_mode="r")
+    samples = {"rows": [0, 1, 4097, 8192, 16383], "cols": [0, 5, 1000, 8191, 16383]}
+    samples["pot"] = [[float(pot3[r, c]) for c in samples["cols"]] for r in samples["rows"]]
+    samples["vel"] = [[[float(vel3[r, c, 0]), float(vel3[r, c, 1])] for c in samples["cols"]] for r in samples["rows"]]
+    meta["c3_samples"] = samples
+    # C3 as a multi-octave field (README.md:28-36, extras/test.py:18-21: separate commands, summed by numpy in
+    # FP32): a 2048 x 24 corner of the 4-octave sum at 16384 x 16384 -- what a fused multi-octave kernel must match
+    octs = [("1.0", "8.0", "0"), ("0.5", "16.0", "1"), ("0.25", "32.0", "2"), ("0.125", "64.0", "3")]
+    total = np.array(pot3[:24, :2048])
+    for amp, freq, seed in octs[1:]:
+        run("generate_simplex", "16384x16384", amp, freq, seed, "oct.npy")
+        total = total + np.load(os.path.join(tmp, "oct.npy"), mmap_mode="r")[:24, :2048]
+    assert total.dtype == np.float32
+    meta["c3_octaves"] = [[float(a), float(f), int(s)] for a, f, s in octs]
+    del pot3, vel3
+    # C5: splat_points sweep, smallest size (1 M uniform points on 16384 x 8192, k = 3): SURVEY.md 8(c)
+    rng5 = np.random.default_rng(0)
+    x = rng5.random(1 << 20, dtype=np.float32) * np.float32(16384)
+    y = rng5.random(1 << 20, dtype=np.float32) * np.float32(8192)
+    np.save(os.path.join(tmp, "pts_c5.npy"), np.stack([x, y], axis=1))
+    run("splat_points", "pts_c5.npy", "16384x8192", "u8disk", "3", "1.0", "splat_c5.npy")
+    img5 = load("splat_c5.npy")
+    meta["c5_k3_1M"] = {"nonzero": int(np.count_nonzero(img5)), "max": int(img5.max()),
+                        "histogram": np.bincount(img5.ravel(), minlength=256).tolist()}
+    assert meta["c5_k3_1M"]["nonzero"] == 9111185 and meta["c5_k3_1M"]["max"] == 249, "C5 differs from SURVEY.md 8(c)"
     rng = np.random.default_rng(1)
     mask = rng.standard_normal((60, 100)).astype(np.float32)
     cpts = ((rng.random((5000, 2)) * 1.2 - 0.1) * [100, 60]).astype(np.float32)
@@ -131,6 +212,7 @@ def main():
     nxt["cull_mask"], nxt["cull_pts"], nxt["cull_out"] = mask, cpts, load("culled.npy")
     meta["cull"] = {"stdout": out.strip()}
     np.savez_compressed(os.path.join(HERE, "next_small.npz"), **nxt)
+    np.savez_compressed(os.path.join(HERE, "c3_octaves_corner.npz"), total=total)
 
     # ---- scalar goldens SURVEY.md 8(c) lists ---------------------------------------------------
     meta["age_offsets_first10"] = {"240": [131, 142, 171, 202, 144, 205, 130, 203, 101, 149],
