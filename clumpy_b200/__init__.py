@@ -98,6 +98,9 @@ SIGNATURES = {
     "clumpy_cuda_advect_points": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                             C.c_uint32, C.c_uint32, C.c_float, C.c_int, C.c_float,
                                             C.c_int, C.c_uint32, C.c_void_p, FRAME_FN, C.c_void_p]),
+    "clumpy_cuda_advect_points_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                  C.c_uint32, C.c_uint32, C.c_float, C.c_int, C.c_float,
+                                                  C.c_int, C.c_uint32, C.c_void_p, FRAME_FN, C.c_void_p]),
 }
 
 CELLS_AUTO, CELLS_COUNT, CELLS_F16, CELLS_U32, CELLS_EXACT = 0, 1, 2, 3, 4
@@ -154,6 +157,27 @@ def _vp(a):
     if isinstance(a, (int, np.integer)):
         return C.c_void_p(int(a))
     return C.c_void_p(a.ctypes.data)
+
+
+def advect_points_multi(devices, pts, vel, step_size, kernel_size, decay, nframes, on_frame=None):
+    """The whole `clumpy advect_points` command on several GPUs from this process (clumpy_cuda_advect_points_multi);
+    returns (nframes, H, W) u8 unless on_frame(animframe, pixels) consumes the frames."""
+    pts, vel = _f32(pts), _f32(vel)
+    h, w = vel.shape[:2]
+    wrapx, decay = (1, -decay) if decay < 0 else (0, decay)
+    frames = None if on_frame else np.empty((nframes, h, w), np.uint8)
+
+    def cb(_user, animframe, pixels):
+        px = np.ctypeslib.as_array(pixels, shape=(h, w))
+        if on_frame:
+            return int(on_frame(animframe, px) or 0)
+        frames[animframe] = px
+        return 0
+
+    devs = (C.c_int * len(devices))(*devices)
+    _check(lib().clumpy_cuda_advect_points_multi(devs, len(devices), _vp(pts), len(pts), _vp(vel), w, h, step_size,
+                                                 kernel_size, decay, wrapx, nframes, None, FRAME_FN(cb), None))
+    return frames
 
 
 def age_offsets(nframes, npts):

@@ -100,6 +100,7 @@ struct clumpy_advect {
     uint32_t* hist_buf[MAX_HIST] = {};
     int fuse = 1;                           // simulation frames per advect launch
     bool overlap = false, side_dirty = false;
+    int overlap_opt = -1;     // what the caller asked for: 1 on, 0 off, -1 automatic
     bool keep_pos = false;    // positions / phases are accessed with the normal L2 policy instead of
                               // evict-first (when the whole working set of a rank fits in L2)
     // group path (half cells): set g % 3 of group g; composite(g) zeroes the images group g - 1 used
@@ -287,9 +288,11 @@ static int sort_points(clumpy_advect* a, int regroup_opt) {
 
     SortGrid sg;
     sg.width = a->width; sg.height = a->height;
-    // 8 x 4 texels per tile (measured best on B200 among 8x4, 16x2, 16x4, 32x1, 16x1).
-    // CLUMPY_CUDA_SORT_TILE="sx,sy" (log2) overrides (A/B runs).
-    sg.shift_x = 3; sg.shift_y = 2;
+    // 16 x 2 texels per tile: a tile row is one 32-byte sector of half cells and one 128-byte line of the field
+    // (measured on B200, C4, steady state: 16x2 0.0775 ms per frame for the advect launch, 8x4 0.0820, 8x2 0.0800,
+    // 16x4 0.0796, 32x1 0.0798, 4x4 0.0882; profiles/r2_sweep_single.jsonl).  CLUMPY_CUDA_SORT_TILE="sx,sy" (log2)
+    // overrides (A/B runs).
+    sg.shift_x = 4; sg.shift_y = 1;
     if (const char* t = getenv("CLUMPY_CUDA_SORT_TILE")) {
         int sx = 0, sy = 0;
         if (sscanf(t, "%d,%d", &sx, &sy) == 2 && sx >= 0 && sx < 12 && sy >= 0 && sy < 12) { sg.shift_x = sx; sg.shift_y = sy; }
@@ -426,8 +429,13 @@ static int advect_begin_impl(clumpy_advect* a, const clumpy_advect_desc& d) {
     int rc = choose_cells(a, d.cells);
     if (rc) return rc;
     {
+        // The composite work of a group may run on a side stream next to the advect launch of the next group.
+        // With both stages bound by DRAM (round 2: profiles/r2_ncu_steady_summary.txt) that buys nothing in the
+        // steady state (C4: 0.1417 ms per frame overlapped, 0.1293 one after the other), so it is off unless asked
+        // for; the multi-GPU path, whose stages wait for other GPUs, always overlaps (route_begin).
         const int ov = env_int("CLUMPY_CUDA_OVERLAP", d.overlap > 0 ? 1 : d.overlap < 0 ? 0 : -1);
-        a->overlap = ov >= 0 ? ov != 0 : a->npts >= (1u << 18);
+        a->overlap_opt = ov;
+        a->overlap = ov > 0;
         a->keep_pos = env_int("CLUMPY_CUDA_KEEP_POS", 0) == 1;
     }
     // Counter images.  Half cells: three sets of `fuse` images; while the images of group g are composited
@@ -991,6 +999,7 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     // which fits in the 32 slack rows of its band buffer.
     rt.chunk = (int)round_up(ceil_div(adv->height, (uint32_t)world), 16);
     REQUIRE(world == 1 || rt.chunk >= 2 * adv->geom.halo, "bands thinner than the sprite are not supported");
+    if (adv->overlap_opt < 0) adv->overlap = true; // the receiving half waits for other GPUs: keep it off the main stream
     rt.fuse = std::min(std::max(env_int("CLUMPY_ROUTE_FUSE", adv->cell_mode == CELL_F16 ? ROUTE_MAX_FUSE : 4), 1), ROUTE_MAX_FUSE);
     rt.minb = env_int("CLUMPY_ROUTE_MINB", 6) == 8 ? 8 : 6;
     rt.timeout_ns = (unsigned long long)std::max(1, env_int("CLUMPY_ROUTE_TIMEOUT_MS", 2000)) * 1000000ull;

@@ -101,6 +101,21 @@ bool AdvectPoints::exec(vector<string> args) {
         return false;
     }
 
+    const vector<int> devices = clumpy_devices();
+    if (!devices.empty()) { // several GPUs of this box, driven from this process
+        FrameSink sink{suffix, width, height, nframes};
+        for (uint32_t s = 0; s < nframes; ++s) show_progress(s, 2 * nframes);
+        const int rc = clumpy_cuda_advect_points_multi(devices.data(), (int)devices.size(), pts.data<float>(), npts, vel.data<float>(),
+                                                       width, height, step_size, kernel_size, decay, advect_wrapx ? 1 : 0, nframes,
+                                                       /*age_offset=*/nullptr, write_frame, &sink);
+        if (sink.failed) {
+            printf("\nCould not write frame %03u%s\n", sink.written, suffix.c_str());
+            return false;
+        }
+        if (!Gpu::report(rc)) return false;
+        printf("\nGenerated %03d%s through %03u%s.\n", 0, suffix.c_str(), nframes - 1, suffix.c_str());
+        return true;
+    }
     Gpu gpu;
     if (!gpu) return false;
     FrameSink sink{suffix, width, height, nframes};

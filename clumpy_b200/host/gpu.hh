@@ -6,6 +6,27 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
+
+// CLUMPY_DEVICES="0,1,2,3" or "0-7": the GPUs a command may spread over (advect_points does; one process drives
+// them all).  Empty when unset or naming a single device (then CLUMPY_DEVICE / device 0 is used as before).
+inline std::vector<int> clumpy_devices() {
+    std::vector<int> out;
+    const char* s = getenv("CLUMPY_DEVICES");
+    if (!s) return out;
+    while (*s) {
+        char* end = nullptr;
+        const long a = strtol(s, &end, 10);
+        if (end == s) break;
+        long b = a;
+        s = end;
+        if (*s == '-') { b = strtol(s + 1, &end, 10); s = end; }
+        for (long d = a; d <= b && out.size() < 8; ++d) out.push_back((int)d);
+        if (*s == ',') ++s; else break;
+    }
+    if (out.size() < 2) out.clear();
+    return out;
+}
 
 struct Gpu {
     clumpy_cuda_ctx* ctx = nullptr;

@@ -340,6 +340,18 @@ int clumpy_cuda_advect_points(clumpy_cuda_ctx* ctx, const float* pts_host, uint3
                               uint32_t nframes, const uint32_t* age_offset,
                               clumpy_frame_fn on_frame, void* user);
 
+/* The same command on `ndevices` GPUs of one box, driven from this one process (commands/advect_points.cc:137-179
+ * behind the same plugin interface: `clumpy advect_points` calls it when CLUMPY_DEVICES lists several devices).
+ * One context per device, peer access between all of them, points sharded by home row on the devices, reset
+ * offsets drawn once, the routed frame loop above, every GPU copying its row band of each recorded frame over its
+ * own PCIe link; the bands are stitched on the host and handed to on_frame in order.  A device may be listed more
+ * than once (the ranks then share it). */
+int clumpy_cuda_advect_points_multi(const int* devices, int ndevices, const float* pts_host, uint32_t npts,
+                                    const float* vel_host, uint32_t width, uint32_t height,
+                                    float step_size, int kernel_size, float decay, int wrapx,
+                                    uint32_t nframes, const uint32_t* age_offset,
+                                    clumpy_frame_fn on_frame, void* user);
+
 #ifdef __cplusplus
 }
 #endif

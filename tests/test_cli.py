@@ -21,8 +21,8 @@ def cli():
         subprocess.run(["make", "-s", "-C", ROOT, "cli"], check=True)
 
     def run(*args, cwd=None):
-        p = subprocess.run([CLI] + [str(a) for a in args], cwd=cwd, capture_output=True, text=True)
-        return p.returncode, p.stdout
+        p = subprocess.run([CLI] + [str(a) for a in args], cwd=cwd, capture_output=True)
+        return p.returncode, p.stdout.decode(errors="replace")  # (bytes as printed: no newline translation of the \r's)
     return run
 
 

@@ -179,3 +179,52 @@ def test_dead_peer_times_out_instead_of_hanging(oracle_mod, monkeypatch):
             a.close()
         for c in run.ctxs:
             c.close()
+
+
+# ---- the C++ driver behind `clumpy advect_points` with CLUMPY_DEVICES: several ranks from one process ---------------
+
+@pytest.mark.parametrize("devices,w,h,n,k,decay,nframes,step", [
+    ([0, 0], 320, 200, 60000, 3, 0.97, 9, 40.0),
+    ([0, 0, 0], 256, 160, 30000, 1, 0.9, 70, 40.0),     # more frames than one turn of the warm-up loop, regroups inside
+    ([0, 0, 0, 0], 200, 136, 9000, 5, -0.95, 5, 30.0),  # 32-bit cells, x-wrap
+    ([0], 128, 96, 20000, 3, 0.95, 4, 25.0),            # a world of one
+])
+def test_single_process_driver_matches_oracle(oracle_mod, devices, w, h, n, k, decay, nframes, step):
+    """clumpy_cuda_advect_points_multi (advect_points.cc:137-179 on several GPUs from one process; here the "GPUs"
+    are the same device listed several times): every recorded frame against the oracle's."""
+    import clumpy_b200
+    vel = _field(oracle_mod, w, h)
+    pts = ((np.random.default_rng(33).random((n, 2)) * 1.04 - 0.02) * [w, h]).astype(np.float32)
+    frames = clumpy_b200.advect_points_multi(devices, pts, vel, step, k, decay, nframes)
+    ref = oracle_mod.Advect(pts, vel, step, k, decay, nframes)
+    try:
+        for _ in range(nframes):
+            ref.step()
+        for f in range(nframes):
+            ref.step()
+            frac, worst = frame_agreement(frames[f], ref.image())
+            assert frac >= 0.999, (f, frac, worst)
+            if k == 1:
+                assert worst == 0, f
+    finally:
+        ref.close()
+
+
+def test_cli_advect_points_on_several_devices(golden, tmp_path):
+    """`CLUMPY_DEVICES=0,0 clumpy advect_points ...` (README example5, k = 1): the same 240 files, byte for byte, as
+    the reference CLI and as the one-GPU run."""
+    import hashlib
+    import subprocess
+    import oracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pot, _, _ = oracle.generate_simplex(1000, 500, 1.0, 8.0, 0)
+    vel, _, _ = oracle.curl_2d(pot)
+    np.save(tmp_path / "velocity.npy", vel)
+    np.save(tmp_path / "pts.npy", golden["c1_pts"])
+    env = dict(os.environ, CLUMPY_DEVICES="0,0")
+    p = subprocess.run([os.path.join(root, "clumpy_b200", "clumpy"), "advect_points", "pts.npy", "velocity.npy", "30", "1", "0.95", "240", "anim.npy"],
+                       cwd=tmp_path, env=env, capture_output=True)
+    assert p.returncode == 0, p.stdout.decode(errors="replace")[-300:]
+    assert hashlib.md5(p.stdout).hexdigest() == golden["meta"]["c1_advect_stdout_md5"]
+    got = [hashlib.md5(open(tmp_path / f"{i:03}anim.npy", "rb").read()).hexdigest() for i in range(240)]
+    assert got == golden["meta"]["c1_frame_md5"]
