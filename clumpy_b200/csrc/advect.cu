@@ -204,7 +204,7 @@ static void advect_release(clumpy_advect* a) {
     if (!a) return;
     clumpy_cuda_ctx* ctx = a->ctx;
     cudaSetDevice(ctx->device);
-    for (cudaStream_t s : {ctx->stream, ctx->aux_stream, ctx->aux2_stream, ctx->copy_stream}) cudaStreamSynchronize(s);
+    for (cudaStream_t s : {ctx->stream, ctx->aux_stream, ctx->copy_stream}) cudaStreamSynchronize(s);
     for (void* p : {(void*)a->pos, (void*)a->orig, a->offset, (void*)a->perm, (void*)a->pos_alt, (void*)a->orig_alt,
                     a->offset_alt, (void*)a->perm_alt, (void*)a->sort_counts, (void*)a->sort_sums, (void*)a->hist,
                     (void*)a->route.band, (void*)a->route.ticket})
@@ -1314,7 +1314,7 @@ CLUMPY_API int clumpy_cuda_advect_route_errors(clumpy_advect* adv, uint32_t* err
     REQUIRE(adv && errors && adv->route.on, "routing is not set up");
     clumpy_cuda_ctx* ctx = adv->ctx;
     CK(cudaSetDevice(ctx->device));
-    for (cudaStream_t s : {ctx->stream, ctx->aux_stream, ctx->aux2_stream}) CK(cudaStreamSynchronize(s));
+    for (cudaStream_t s : {ctx->stream, ctx->aux_stream}) CK(cudaStreamSynchronize(s));
     *errors = *reinterpret_cast<volatile uint32_t*>(adv->route.errors);
     return CLUMPY_OK;
 }

@@ -122,7 +122,6 @@ static int create_impl(clumpy_cuda_ctx* ctx, int device, void* stream, const cud
         int least = 0, greatest = 0;
         CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
         CK(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, greatest));
-        CK(cudaStreamCreateWithPriority(&ctx->aux2_stream, cudaStreamNonBlocking, greatest));
     }
     CK(cudaEventCreate(&ctx->t0));
     CK(cudaEventCreate(&ctx->t1));
@@ -144,7 +143,7 @@ CLUMPY_API void clumpy_cuda_destroy(clumpy_cuda_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (cudaStream_t s : {ctx->copy_stream, ctx->aux_stream, ctx->aux2_stream})
+    for (cudaStream_t s : {ctx->copy_stream, ctx->aux_stream})
         if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
@@ -161,7 +160,6 @@ CLUMPY_API int clumpy_cuda_sync(clumpy_cuda_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->aux_stream));
-    CK(cudaStreamSynchronize(ctx->aux2_stream));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     return CLUMPY_OK;
 }

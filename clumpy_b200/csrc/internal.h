@@ -60,14 +60,9 @@ struct clumpy_cuda_ctx {
     cudaStream_t stream = nullptr;      // compute stream (caller's or ours)
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr; // frame D2H side stream
-    cudaStream_t aux_stream = nullptr;  // high-priority stream: composite + clear of frame s run here
-                                        // while the advect kernel of frame s+1 runs on `stream`
-    cudaStream_t aux2_stream = nullptr; // second high-priority stream: the multi-GPU path drains inboxes on
-                                        // aux_stream and composites on this one, so that the drain of
-                                        // frame s+1 overlaps the composite of frame s
-    int keep_cells = 0;                 // counters are accessed with L2 evict-last hints
-    int composite_ctas_per_sm = 0;      // >0: cap on resident composite CTAs per SM (leaves room for
-                                        // the advect kernel when the two overlap); 0 = fill the SM
+    cudaStream_t aux_stream = nullptr;  // high-priority side stream: the receiving half of a multi-GPU group (drain +
+                                        // band composite), and the composite work of a single-GPU group when asked
+                                        // to overlap with the next advect launch
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     uint64_t launches = 0;
     uint32_t* d_minmax = nullptr; // 2 order-preserving encoded floats (min, max)

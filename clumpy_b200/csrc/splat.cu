@@ -16,7 +16,7 @@
 // f_a is the reference's per-hit blend (:153-155) with its two roundings and the truncation, so a
 // pixel hit by taps of a single opacity is reproduced bit for bit (k = 1 always).  When several
 // opacities hit the same pixel in one frame the reference interleaves them in point order; replaying
-// ring by ring differs by at most 1 LSB (measured; tests/test_advect_gpu.py checks it).
+// ring by ring differs by at most 1 LSB (measured; tests/test_gpu_parity.py checks it).
 // f_a is monotone on 0..255, so the replay stops as soon as it reaches a fixed point -- at most 255
 // iterations however many points pile up on one pixel.
 //

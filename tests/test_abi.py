@@ -79,3 +79,16 @@ def test_no_silent_cpu_fallback():
         pytest.skip("a GPU is present")
     with pytest.raises(clumpy_b200.ClumpyCudaError):
         clumpy_b200.Context(0)
+
+
+def test_both_build_files_list_every_source():
+    """The Makefile (what build() runs) and CMakeLists.txt (the sm_100a CMake target) compile the same sources."""
+    csrc = os.path.join(ROOT, "clumpy_b200", "csrc")
+    sources = sorted(f for f in os.listdir(csrc) if f.endswith((".cu", ".cc")))
+    make = open(os.path.join(ROOT, "Makefile")).read()
+    cmake = open(os.path.join(ROOT, "CMakeLists.txt")).read()
+    for f in sources:
+        stem = f.rsplit(".", 1)[0]
+        assert f in cmake, f
+        assert f in make or f"{stem}.o" in make, f
+    assert "CMAKE_CUDA_ARCHITECTURES 100a" in cmake and "compute_100a,code=sm_100a" in make

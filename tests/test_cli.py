@@ -193,7 +193,7 @@ def test_splat_points_cli(cli, golden, tmp_path):
         rc, out = cli("splat_points", "pts.npy", "96x64", "u8disk", c["k"], c["alpha"], f"{name}.npy", cwd=tmp_path)
         assert rc == 0 and out.strip() == c["stdout"] == f"Drawing {len(spl['pts'])} points."
         raw = open(tmp_path / f"{name}.npy", "rb").read()
-        assert raw[:8] == b"\x93NUMPY\x01\x00" and b"'descr': '|u1'" in raw[:80] and b"'shape': (64, 96), }" in raw[:80]
+        assert raw[:8] == b"\x93NUMPY\x01\x00" and b"'descr': '<u1'" in raw[:80] and b"'shape': (64, 96), }" in raw[:80]
         assert (len(raw) - 64 * 96) % 16 == 0
         got = np.load(tmp_path / f"{name}.npy")
         d = np.abs(got.astype(int) - spl[name].astype(int))
@@ -220,7 +220,7 @@ def test_advect_points_cli_frames_of_the_small_fixtures(cli, golden, tmp_path):
         ref = adv[f"frames_{name}"]
         for f in range(c["nframes"]):
             raw = open(tmp_path / f"{f:03}_{name}.npy", "rb").read()
-            assert b"'descr': '|u1'" in raw[:80] and b"'shape': (64, 96), }" in raw[:80]
+            assert b"'descr': '<u1'" in raw[:80] and b"'shape': (64, 96), }" in raw[:80]
             d = np.abs(np.load(tmp_path / f"{f:03}_{name}.npy").astype(int) - ref[f].astype(int))
             assert d.max() <= 1 and (d == 0).mean() >= 0.998, (name, f)
             if c["k"] == 1:

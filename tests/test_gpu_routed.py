@@ -221,7 +221,8 @@ def test_cli_advect_points_on_several_devices(golden, tmp_path):
     vel, _, _ = oracle.curl_2d(pot)
     np.save(tmp_path / "velocity.npy", vel)
     np.save(tmp_path / "pts.npy", golden["c1_pts"])
-    env = dict(os.environ, CLUMPY_DEVICES="0,0")
+    # CLUMPY_TEST_DEVICES=0,1 on a multi-GPU box: the same run over NVLink peer memory
+    env = dict(os.environ, CLUMPY_DEVICES=os.environ.get("CLUMPY_TEST_DEVICES", "0,0"))
     p = subprocess.run([os.path.join(root, "clumpy_b200", "clumpy"), "advect_points", "pts.npy", "velocity.npy", "30", "1", "0.95", "240", "anim.npy"],
                        cwd=tmp_path, env=env, capture_output=True)
     assert p.returncode == 0, p.stdout.decode(errors="replace")[-300:]
