@@ -489,18 +489,29 @@ def run_multi(args):
     band_rows = -(-h // world) + 32
 
     def e2e_once(nr, host_frames):
+        t_e2e = time.perf_counter()
+
+        def lap(what):  # CLUMPY_BENCH_VERBOSE=1: where the end-to-end time goes (synchronises: perturbs the run)
+            if os.environ.get("CLUMPY_BENCH_VERBOSE") == "1":
+                torch.cuda.synchronize()
+                note(f"e2e +{(time.perf_counter() - t_e2e) * 1e3:8.2f} ms  {what}")
+
         d_pts = pts.to(device, non_blocking=True)                   # H2D: all points (the shard is selected on the device)
         d_band = vel_band.to(device, non_blocking=True)             # H2D: this rank's rows of the field
         field = torch.empty((world, vel_band.shape[0], w, 2), dtype=torch.float32, device=device)
         dist.all_gather_into_tensor(field, d_band)                  # NVLink: every rank gets the whole field
         field = field.reshape(-1, w, 2) if h % world == 0 else torch.cat(
             [field[r, :mg.field_rows(h, world, r)[1] - mg.field_rows(h, world, r)[0]] for r in range(world)])
+        lap("points + field band uploaded, field all-gathered")
         r2 = make_run(d_pts, field, nr)                              # offsets on a host thread, shard select, sort, IPC handles
+        lap("sharded run set up")
         r2.step(nr)                                                  # warm-up half
         r2.record(nr, host_frames, host_frames.shape[1] * w)         # recorded half: D2H of the band of every frame
         torch.cuda.synchronize()
         r2.adv.wait_frames()
+        lap("frames done")
         r2.close()
+        lap("closed")
 
     host_frames = torch.empty((nrec, band_rows, w), dtype=torch.uint8).pin_memory()
     e2e_once(min(2, nrec), host_frames)  # untimed warm-up call (module load, memory pool, pinned staging, NCCL buffers)

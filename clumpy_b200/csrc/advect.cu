@@ -1014,7 +1014,9 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     rt.cnt_offset = (size_t)ROUTE_PARITIES * ROUTE_MAX_FUSE * rt.entries_per_frame;
     rt.flags_offset = round_up(rt.cnt_offset + (size_t)ROUTE_PARITIES * ROUTE_MAX_FUSE * rt.cnt_per_frame, 64);
     const size_t ibytes = round_up((rt.flags_offset + (size_t)ROUTE_MAX_WORLD) * sizeof(uint32_t), 256);
+    trace_mark(ctx, "route_begin: start");
     CK(cudaMalloc(&rt.inbox, ibytes)); // mapped by the peers: a plain allocation, not the pool
+    trace_mark(ctx, "route_begin: inbox allocation");
     DEV_ALLOC(ctx, &rt.band, (size_t)NSETS * ROUTE_MAX_FUSE * rt.band_bytes);
     for (int s = 0; s < NSETS; ++s) CK(cudaEventCreateWithFlags(&rt.composited[s], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&rt.routed, cudaEventDisableTiming));
@@ -1059,6 +1061,7 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
         }
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    trace_mark(ctx, "route_begin: band buffers, clears, kernels loaded");
     rt.peer_inbox[rank] = rt.inbox;
     // Profiling aid (ncu must not run a multi-rank job): with CLUMPY_ROUTE_LOOPBACK=1 one process plays
     // rank `rank` of `world` alone.  The caller maps its own inbox as every peer's; the fence then
@@ -1164,7 +1167,7 @@ static int route_group(clumpy_advect* adv, uint32_t nf, RecordSink* sink, RouteE
         dd.wrap_w = adv->wrapx ? (int)adv->width : 0; dd.halo = adv->geom.halo; dd.pitch = adv->geom.pitch;
         // A small grid: these CTAs may sit waiting for a peer's epoch while route kernels run on the
         // main stream, and must leave them most of the SMs.
-        const uint32_t dgrid = std::min<uint32_t>(256u, std::max<uint32_t>(1u, ceil_div((uint32_t)(nf * rt.cnt_per_frame), 32u * 8u)));
+        const uint32_t dgrid = std::min<uint32_t>(256u, std::max<uint32_t>(1u, ceil_div((uint32_t)rt.cnt_per_frame, 8u))); // a warp per region and frame
         if (adv->cell_mode == CELL_F16) drain_group_kernel<CELL_F16><<<dgrid, 256, 0, side>>>(dd);
         else drain_group_kernel<CELL_U32><<<dgrid, 256, 0, side>>>(dd);
         CK_LAUNCH(ctx);

@@ -381,8 +381,10 @@ drain_group_kernel(DrainDev d) {
         __syncthreads();
         if (!arrived) return;
     }
-    // (frame, source, region) triples are dealt round-robin to the warps in chunks of 32: a warp loads 32
-    // count words in one go (most are zero: far ranks send nothing), then works through the non-empty ones.
+    // The regions of a frame are dealt to the warps ROUND-ROBIN (region c goes to warp c % nwarp): the non-empty
+    // ones are the CTAs near a band edge, which are neighbours in region order, so a contiguous deal would leave
+    // all the work to a few warps.  A warp loads the count words of up to 32 of its regions in one go (most are
+    // zero: far CTAs send nothing), then works through the non-empty ones.
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarp = gridDim.x * (blockDim.x >> 5);
     const uint32_t per_frame = (uint32_t)d.world * d.nregion; // the count words of a frame are contiguous
@@ -390,8 +392,8 @@ drain_group_kernel(DrainDev d) {
         uint32_t* cnt = d.cnt + (size_t)f * d.cnt_frame_stride;
         const uint32_t* inbox = d.inbox + (size_t)f * d.inbox_frame_stride;
         uint32_t* band = d.band[f];
-        for (uint32_t c0 = warp * 32u; c0 < per_frame; c0 += nwarp * 32u) {
-            const uint32_t c = c0 + lane;
+        for (uint32_t k0 = 0; warp + k0 * nwarp < per_frame; k0 += 32u) {
+            const uint32_t c = warp + (k0 + lane) * nwarp;
             uint32_t* word = cnt + c;
             const uint32_t mine = (c < per_frame) ? min(__ldcg(word), ROUTE_REGION) : 0u; // written by a peer: read at L2
             if (mine) *word = 0u;
@@ -400,7 +402,7 @@ drain_group_kernel(DrainDev d) {
                 const int r = __ffs(todo) - 1;
                 todo &= todo - 1u;
                 const uint32_t n = __shfl_sync(0xFFFFFFFFu, mine, r);
-                const uint32_t* seg = inbox + (size_t)(c0 + (uint32_t)r) * ROUTE_REGION;
+                const uint32_t* seg = inbox + (size_t)(warp + (k0 + (uint32_t)r) * nwarp) * ROUTE_REGION;
                 for (uint32_t i0 = 0; i0 < n; i0 += 256u) { // 8 loads in flight per lane: the loop is latency-bound
                     uint32_t e[8];
 #pragma unroll

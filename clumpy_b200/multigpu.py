@@ -16,6 +16,8 @@ gloo backend in tests/test_multigpu_cpu.py; the device work goes through the C A
 (clumpy_cuda_advect_count / _cells / _composite_rows / _finish_frame).
 """
 import os
+import sys
+import time
 
 import numpy as np
 
@@ -268,6 +270,7 @@ class RoutedAdvect:
         d_pts = pts if torch.is_tensor(pts) else torch.from_numpy(np.ascontiguousarray(pts, np.float32)).to(device, non_blocking=True)
         self._vel = vel  # a device field is used in place: keep it alive
         torch.cuda.current_stream().synchronize()
+        self._t0 = time.perf_counter()
         if shard == "home_rows":
             # strips of equal point count, from the row histogram of the whole cloud: every rank computes the
             # same edges from the same points, so nothing is exchanged
@@ -288,6 +291,7 @@ class RoutedAdvect:
         self.adv = ctx.advect(points_arg, vel_arg, step_size, kernel_size, decay, nframes, age_offset=offsets,
                               npts=npts_arg, width=self.w_img, height=self.h_img, cells="count", shard_rows=rows_arg)
         self.sharded_by_rows = rows_arg is not None
+        self._lap("advect_begin_ex (uploads, offsets, shard selection, sort)")
         capacity = max(1, max(self.shard_sizes))
         inbox, _ = self.adv.route_begin(self.rank, self.world, capacity)
         # exchange CUDA IPC handles of the inboxes (64 bytes each, over NCCL) and map the peers'
@@ -303,6 +307,12 @@ class RoutedAdvect:
         self.y0, self.y1 = self.adv.owned_rows()
         if self.world > 1 and not self.loopback:
             dist.barrier()
+        self._lap("inbox allocated, IPC handles exchanged and mapped, barrier")
+
+    def _lap(self, what):  # CLUMPY_BENCH_VERBOSE=1: set-up phases on stderr
+        if os.environ.get("CLUMPY_BENCH_VERBOSE") == "1":
+            self.torch.cuda.synchronize()
+            print(f"[RoutedAdvect rank {self.rank}] +{(time.perf_counter() - self._t0) * 1e3:8.2f} ms  {what}", file=sys.stderr, flush=True)
 
     def step(self, count=1):
         self.adv.route_steps(count)  # fence on the device (epoch flags in peer memory): one call enqueues all the frames
