@@ -56,6 +56,8 @@ SIGNATURES = {
                                            C.c_uint32, C.c_void_p]),
     "clumpy_cuda_splat_disks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
                                           C.c_uint32, C.c_void_p, C.c_float, C.c_int, C.c_int]),
+    "clumpy_cuda_splat_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                          C.c_float, C.c_int, C.c_int]),
     "clumpy_cuda_age_offsets": (C.c_int, [C.c_uint32, C.c_uint32, _u32p]),
     "clumpy_cuda_advect_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                            C.c_uint32, C.c_uint32, C.c_float, C.c_int, C.c_float,
@@ -74,6 +76,7 @@ SIGNATURES = {
     "clumpy_cuda_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "clumpy_cuda_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "clumpy_cuda_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "clumpy_cuda_advect_route_bytes": (C.c_int, [C.c_uint32, C.c_int, C.POINTER(C.c_size_t)]),
     "clumpy_cuda_advect_route_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint32,
                                                  C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "clumpy_cuda_advect_route_peers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -159,6 +162,16 @@ def _vp(a):
     return C.c_void_p(a.ctypes.data)
 
 
+def splat_multi(devices, pts, width, height, alpha, kernel_size, wrapx=False, img=None):
+    """`clumpy splat_points` on several GPUs from this process (clumpy_cuda_splat_multi): fast path when alpha == 1
+    and kernel_size == 1, splat_disks otherwise."""
+    pts = _f32(pts)
+    img = np.zeros((height, width), np.uint8) if img is None else np.ascontiguousarray(img).copy()
+    devs = (C.c_int * len(devices))(*devices)
+    _check(lib().clumpy_cuda_splat_multi(devs, len(devices), _vp(pts), len(pts), width, height, _vp(img), alpha, kernel_size, int(wrapx)))
+    return img
+
+
 def advect_points_multi(devices, pts, vel, step_size, kernel_size, decay, nframes, on_frame=None):
     """The whole `clumpy advect_points` command on several GPUs from this process (clumpy_cuda_advect_points_multi);
     returns (nframes, H, W) u8 unless on_frame(animframe, pixels) consumes the frames."""
@@ -178,6 +191,12 @@ def advect_points_multi(devices, pts, vel, step_size, kernel_size, decay, nframe
     _check(lib().clumpy_cuda_advect_points_multi(devs, len(devices), _vp(pts), len(pts), _vp(vel), w, h, step_size,
                                                  kernel_size, decay, wrapx, nframes, None, FRAME_FN(cb), None))
     return frames
+
+
+def route_inbox_bytes(capacity, world):
+    n = C.c_size_t()
+    _check(lib().clumpy_cuda_advect_route_bytes(capacity, world, C.byref(n)))
+    return n.value
 
 
 def age_offsets(nframes, npts):
@@ -204,6 +223,13 @@ class Context:
 
     def close(self):
         if self._h:
+            arena = getattr(self, "_route_arena", None)
+            if arena:  # the inbox arena kept between routed multi-GPU runs (clumpy_b200/multigpu.py)
+                for p in arena["peers"]:
+                    if p != arena["inbox"]:
+                        lib().clumpy_cuda_ipc_close(self._h, C.c_void_p(p))
+                lib().clumpy_cuda_dev_free(self._h, C.c_void_p(arena["inbox"]))
+                self._route_arena = None
             lib().clumpy_cuda_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -243,6 +269,14 @@ class Context:
 
     def ipc_close(self, dptr):
         _check(lib().clumpy_cuda_ipc_close(self._h, C.c_void_p(int(dptr))))
+
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        _check(lib().clumpy_cuda_dev_alloc(self._h, nbytes, C.byref(p)))
+        return p.value
+
+    def dev_free(self, dptr):
+        _check(lib().clumpy_cuda_dev_free(self._h, C.c_void_p(int(dptr))))
 
     def launch_count(self):
         n = C.c_uint64()
@@ -474,9 +508,10 @@ class Advect:
 
     # ---- exchange fused into the advect kernel (peer-memory inboxes) ----------------------------
 
-    def route_begin(self, rank, world, capacity):
-        """-> (device address, bytes) of this rank's inbox allocation."""
-        p, n = C.c_void_p(), C.c_size_t()
+    def route_begin(self, rank, world, capacity, arena=None):
+        """-> (device address, bytes) of this rank's inbox: allocated by the run, or the caller's `arena` =
+        (device address, bytes) kept from an earlier run."""
+        p, n = C.c_void_p(arena[0] if arena else None), C.c_size_t(arena[1] if arena else 0)
         _check(lib().clumpy_cuda_advect_route_begin(self._h, rank, world, capacity, C.byref(p), C.byref(n)))
         return p.value, n.value
 

@@ -129,6 +129,7 @@ struct clumpy_advect {
         int fuse = ROUTE_MAX_FUSE;   // frames per route launch
         int minb = 6;                // route kernel variant: 6 CTAs per SM (40 registers) or 8 (32)
         uint32_t nregion = 0;        // regions of ROUTE_REGION entry slots per source segment
+        bool inbox_owned = true;     // false: the caller's arena (kept across runs together with the peers' mappings of it)
         uint32_t* inbox = nullptr;   // [ROUTE_PARITIES][ROUTE_MAX_FUSE][world][nregion * ROUTE_REGION] cell indices, then
                                      // [ROUTE_PARITIES][ROUTE_MAX_FUSE][world][nregion] count words, then [world] epoch flags
         size_t entries_per_frame = 0, cnt_per_frame = 0, cnt_offset = 0, flags_offset = 0; // in uint32 units
@@ -214,7 +215,7 @@ static void advect_release(clumpy_advect* a) {
         dev_release(ctx, a->imgs[i]);
         if (a->copy_done[i]) cudaEventDestroy(a->copy_done[i]);
     }
-    cudaFree(a->route.inbox); // peers map it: a plain allocation
+    if (a->route.inbox_owned) cudaFree(a->route.inbox); // peers map it: a plain allocation
     if (a->route.errors) cudaFreeHost(a->route.errors);
     for (int s = 0; s < NSETS; ++s) {
         if (a->set_composited[s]) cudaEventDestroy(a->set_composited[s]);
@@ -386,6 +387,7 @@ static int advect_begin_impl(clumpy_advect* a, const clumpy_advect_desc& d) {
     } else {
         DEV_ALLOC(ctx, &a->vel, npix * 8);
         CK(cudaMemcpyAsync(a->vel, d.vel, npix * 8, cudaMemcpyHostToDevice, ctx->stream));
+        trace_mark(ctx, "advect_begin: field upload");
     }
 
     // the caller's points on the device
@@ -400,6 +402,7 @@ static int advect_begin_impl(clumpy_advect* a, const clumpy_advect_desc& d) {
         DEV_ALLOC(ctx, &d_in_own, (size_t)n_in * 8);
         CK(cudaMemcpyAsync(d_in_own, d.pts, (size_t)n_in * 8, cudaMemcpyHostToDevice, ctx->stream));
         d_in = d_in_own;
+        trace_mark(ctx, "advect_begin: point upload");
     }
     // which of them this run simulates
     const bool shard = d.shard_row_hi > d.shard_row_lo;
@@ -426,8 +429,10 @@ static int advect_begin_impl(clumpy_advect* a, const clumpy_advect_desc& d) {
     DEV_ALLOC(ctx, &a->offset, nalloc * 4);
     DEV_ALLOC(ctx, &a->perm, nalloc * 4);
 
+    trace_mark(ctx, "advect_begin: point arrays allocated");
     int rc = choose_cells(a, d.cells);
     if (rc) return rc;
+    trace_mark(ctx, "advect_begin: cell type chosen, replay table built");
     {
         // The composite work of a group may run on a side stream next to the advect launch of the next group.
         // With both stages bound by DRAM (round 2: profiles/r2_ncu_steady_summary.txt) that buys nothing in the
@@ -979,6 +984,26 @@ static void launch_route_t(clumpy_advect* a, const RouteDev& rd) {
             a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);
 }
 
+static size_t route_inbox_layout(uint32_t capacity, int world, uint32_t* nregion, size_t* entries_per_frame, size_t* cnt_per_frame,
+                                 size_t* cnt_offset, size_t* flags_offset) {
+    const uint32_t nr = std::max<uint32_t>(ceil_div(capacity, ROUTE_BLOCK), 1u); // one region per CTA of the largest shard
+    const size_t epf = (size_t)world * nr * ROUTE_REGION, cpf = (size_t)world * nr;
+    const size_t co = (size_t)ROUTE_PARITIES * ROUTE_MAX_FUSE * epf;
+    const size_t fo = round_up(co + (size_t)ROUTE_PARITIES * ROUTE_MAX_FUSE * cpf, 64);
+    if (nregion) *nregion = nr;
+    if (entries_per_frame) *entries_per_frame = epf;
+    if (cnt_per_frame) *cnt_per_frame = cpf;
+    if (cnt_offset) *cnt_offset = co;
+    if (flags_offset) *flags_offset = fo;
+    return round_up((fo + (size_t)ROUTE_MAX_WORLD) * sizeof(uint32_t), 256);
+}
+
+CLUMPY_API int clumpy_cuda_advect_route_bytes(uint32_t capacity, int world, size_t* inbox_bytes) {
+    REQUIRE(inbox_bytes && world >= 1 && world <= ROUTE_MAX_WORLD, "bad argument");
+    *inbox_bytes = route_inbox_layout(capacity, world, nullptr, nullptr, nullptr, nullptr, nullptr);
+    return CLUMPY_OK;
+}
+
 CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int world, uint32_t capacity,
                                               void** inbox_dev, size_t* inbox_bytes) {
     REQUIRE(adv && inbox_dev && inbox_bytes, "null argument");
@@ -991,7 +1016,7 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     CK(cudaSetDevice(ctx->device));
     auto& rt = adv->route;
     rt.rank = rank; rt.world = world;
-    rt.nregion = std::max<uint32_t>(ceil_div(capacity, ROUTE_BLOCK), 1u); // one region per CTA of the largest shard
+    const size_t ibytes = route_inbox_layout(capacity, world, &rt.nregion, &rt.entries_per_frame, &rt.cnt_per_frame, &rt.cnt_offset, &rt.flags_offset);
     // Bands of `chunk` padded rows, whole 16-row tiles, chosen from the IMAGE height so that for a uniform
     // cloud they coincide with the home-row strips of the shards (4096 rows on 8 ranks: 512 each, not the 528
     // that an even split of the 4098 padded rows would give: with those, rank 7 would start with a fifth of
@@ -1009,13 +1034,14 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     const size_t band_rows = (size_t)rt.chunk + 2 * adv->geom.halo + 32;
     rt.band_cells = (uint32_t)(band_rows * adv->geom.pitch);
     rt.band_bytes = round_up((size_t)rt.band_cells * cell_bytes, 256);
-    rt.entries_per_frame = (size_t)world * rt.nregion * ROUTE_REGION;
-    rt.cnt_per_frame = (size_t)world * rt.nregion;
-    rt.cnt_offset = (size_t)ROUTE_PARITIES * ROUTE_MAX_FUSE * rt.entries_per_frame;
-    rt.flags_offset = round_up(rt.cnt_offset + (size_t)ROUTE_PARITIES * ROUTE_MAX_FUSE * rt.cnt_per_frame, 64);
-    const size_t ibytes = round_up((rt.flags_offset + (size_t)ROUTE_MAX_WORLD) * sizeof(uint32_t), 256);
     trace_mark(ctx, "route_begin: start");
-    CK(cudaMalloc(&rt.inbox, ibytes)); // mapped by the peers: a plain allocation, not the pool
+    if (*inbox_dev) { // the caller's arena from an earlier run (its peers still have it mapped)
+        REQUIRE(*inbox_bytes >= ibytes, "the inbox arena passed in is too small for this run");
+        rt.inbox = static_cast<uint32_t*>(*inbox_dev);
+        rt.inbox_owned = false;
+    } else {
+        CK(cudaMalloc(&rt.inbox, ibytes)); // mapped by the peers: a plain allocation, not the pool
+    }
     trace_mark(ctx, "route_begin: inbox allocation");
     DEV_ALLOC(ctx, &rt.band, (size_t)NSETS * ROUTE_MAX_FUSE * rt.band_bytes);
     for (int s = 0; s < NSETS; ++s) CK(cudaEventCreateWithFlags(&rt.composited[s], cudaEventDisableTiming));
@@ -1070,7 +1096,7 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     rt.loopback = env_int("CLUMPY_ROUTE_LOOPBACK", 0) == 1;
     rt.on = true;
     *inbox_dev = rt.inbox;
-    *inbox_bytes = ibytes;
+    if (rt.inbox_owned) *inbox_bytes = ibytes;
     return CLUMPY_OK;
 }
 

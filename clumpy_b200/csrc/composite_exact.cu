@@ -117,25 +117,25 @@ composite_exact_kernel(GeomDev g, ExactSprite sp, const unsigned long long* __re
 // one 64-bit add per point of a plain (N, 2) list: count + original index
 template <bool WRAP>
 __global__ void __launch_bounds__(256)
-exact_count_kernel(const float2* __restrict__ pts, uint32_t npts, GeomDev g, unsigned long long* __restrict__ cells) {
+exact_count_kernel(const float2* __restrict__ pts, uint32_t npts, uint32_t index_base, GeomDev g, unsigned long long* __restrict__ cells) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npts; i += gridDim.x * blockDim.x) {
         const float2 p = pts[i];
         const long long at = hist_index<WRAP>(f2i32_x86(p.x), f2i32_x86(p.y), g);
-        if (at >= 0) atomicAdd(cells + at, ((unsigned long long)i << 24) | 1ull);
+        if (at >= 0) atomicAdd(cells + at, ((unsigned long long)(index_base + i) << 24) | 1ull);
     }
 }
 
 bool exact_mode_supported(int kernel_size, uint64_t npts) { return kernel_size <= 15 && npts < (1ull << 24); }
 
 int launch_exact_count(clumpy_cuda_ctx* ctx, const float* d_pts, uint32_t npts, const HistGeom& hg, int wrapx,
-                       void* d_cells) {
+                       void* d_cells, uint32_t index_base) {
     if (npts == 0) return CLUMPY_OK;
     const GeomDev g{hg.width, hg.height, hg.halo, hg.pitch};
     const uint32_t grid = std::min<uint32_t>(ceil_div(npts, 256), (uint32_t)ctx->sm_count * 16);
     const float2* p = reinterpret_cast<const float2*>(d_pts);
     unsigned long long* c = reinterpret_cast<unsigned long long*>(d_cells);
-    if (wrapx) exact_count_kernel<true><<<grid, 256, 0, ctx->stream>>>(p, npts, g, c);
-    else exact_count_kernel<false><<<grid, 256, 0, ctx->stream>>>(p, npts, g, c);
+    if (wrapx) exact_count_kernel<true><<<grid, 256, 0, ctx->stream>>>(p, npts, index_base, g, c);
+    else exact_count_kernel<false><<<grid, 256, 0, ctx->stream>>>(p, npts, index_base, g, c);
     CK_LAUNCH(ctx);
     return CLUMPY_OK;
 }

@@ -166,8 +166,9 @@ int launch_composite_group(clumpy_cuda_ctx* ctx, cudaStream_t stream, const Grou
 
 // ---- exact-order path for sparse clouds (composite_exact.cu): 64-bit cells = count + index sum ----
 bool exact_mode_supported(int kernel_size, uint64_t npts);
+// index_base: the original index of d_pts[0] (a shard of a longer list: the cells carry ORIGINAL indices)
 int launch_exact_count(clumpy_cuda_ctx* ctx, const float* d_pts, uint32_t npts, const HistGeom& g,
-                       int wrapx, void* d_cells);
+                       int wrapx, void* d_cells, uint32_t index_base = 0);
 int launch_composite_exact(clumpy_cuda_ctx* ctx, const HistGeom& g, const SpriteRings& rings,
                            const void* d_cells, int wrapx, int apply_decay, float decay,
                            const uint8_t* d_img_in, uint8_t* d_img_out);

@@ -62,6 +62,13 @@ bool SplatPoints::exec(vector<string> args) {
         printf("Only disks are implemented right now.\n");
         return false;
     }
+    const vector<int> devices = clumpy_devices();
+    if (!devices.empty()) { // several GPUs of this box, driven from this process
+        if (!Gpu::report(clumpy_cuda_splat_multi(devices.data(), (int)devices.size(), arr.data<float>(), npts, width, height,
+                                                 dstimg.data(), alpha, kernel_size, advect_wrapx ? 1 : 0)))
+            return false;
+        return npy::save_u8(args[5], dstimg.data(), {height, width});
+    }
     Gpu gpu;
     if (!gpu) return false;
     int rc;

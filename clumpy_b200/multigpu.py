@@ -293,16 +293,28 @@ class RoutedAdvect:
         self.sharded_by_rows = rows_arg is not None
         self._lap("advect_begin_ex (uploads, offsets, shard selection, sort)")
         capacity = max(1, max(self.shard_sizes))
-        inbox, _ = self.adv.route_begin(self.rank, self.world, capacity)
-        # exchange CUDA IPC handles of the inboxes (64 bytes each, over NCCL) and map the peers'
+        # The inbox arena and the peers' mappings of it are kept in the context across runs (like a communicator):
+        # exporting, exchanging and mapping a 2 GB allocation costs ~20 ms, more than a short run.  Every rank takes
+        # the same decision: the size depends on world and capacity only.
+        import clumpy_b200
+        need = clumpy_b200.route_inbox_bytes(capacity, self.world)
         if self.loopback or self.world == 1:
+            inbox, _ = self.adv.route_begin(self.rank, self.world, capacity)
             self.peer_ptrs = [inbox] * self.world
         else:
-            mine = torch.frombuffer(bytearray(ctx.ipc_export(inbox)), dtype=torch.uint8).to(device)
-            handles = torch.empty((self.world, 64), dtype=torch.uint8, device=device)
-            dist.all_gather_into_tensor(handles, mine)
-            handles = handles.cpu().numpy()
-            self.peer_ptrs = [inbox if r == self.rank else ctx.ipc_open(handles[r].tobytes()) for r in range(self.world)]
+            cache = getattr(ctx, "_route_arena", None)
+            if not (cache and cache["world"] == self.world and cache["bytes"] >= need):
+                _drop_route_arena(ctx, dist)
+                arena = ctx.dev_alloc(need)
+                # exchange CUDA IPC handles of the arenas (64 bytes each, over NCCL) and map the peers'
+                mine = torch.frombuffer(bytearray(ctx.ipc_export(arena)), dtype=torch.uint8).to(device)
+                handles = torch.empty((self.world, 64), dtype=torch.uint8, device=device)
+                dist.all_gather_into_tensor(handles, mine)
+                handles = handles.cpu().numpy()
+                peers = [arena if r == self.rank else ctx.ipc_open(handles[r].tobytes()) for r in range(self.world)]
+                cache = ctx._route_arena = {"world": self.world, "inbox": arena, "bytes": need, "peers": peers}
+            self.adv.route_begin(self.rank, self.world, capacity, arena=(cache["inbox"], cache["bytes"]))
+            self.peer_ptrs = cache["peers"]
         self.adv.route_peers(self.peer_ptrs)
         self.y0, self.y1 = self.adv.owned_rows()
         if self.world > 1 and not self.loopback:
@@ -355,13 +367,24 @@ class RoutedAdvect:
         self.torch.cuda.synchronize()
         timeouts = self.adv.route_errors()
         if self.world > 1 and not self.loopback:
-            self.dist.barrier()  # nobody may still be writing into an inbox that is about to go away
-        for r, p in enumerate(self.peer_ptrs):
-            if r != self.rank and p and not self.loopback and self.world > 1:
-                self.ctx.ipc_close(p)
+            self.dist.barrier()  # nobody may still be writing into an inbox that the next run re-uses
         self.adv.close()
         if timeouts:
             raise RuntimeError(f"rank {self.rank}: {timeouts} frame fences timed out (a peer stopped publishing)")
+
+
+def _drop_route_arena(ctx, dist):
+    """Unmaps and frees the inbox arena a context keeps between routed runs (collective: every rank decides alike)."""
+    cache = getattr(ctx, "_route_arena", None)
+    if not cache:
+        return
+    dist.barrier()
+    for p in cache["peers"]:
+        if p != cache["inbox"]:
+            ctx.ipc_close(p)
+    dist.barrier()  # every mapping of my arena is gone before I free it
+    ctx.dev_free(cache["inbox"])
+    ctx._route_arena = None
 
 
 def make_sharded(kind, *a, **kw):

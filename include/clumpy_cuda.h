@@ -156,6 +156,15 @@ int clumpy_cuda_splat_disks(clumpy_cuda_ctx* ctx, const float* pts_host, uint32_
                             uint32_t width, uint32_t height, uint8_t* img_host, float alpha,
                             int kernel_size, int wrapx);
 
+/* The same two rasterisers on `ndevices` GPUs of one box from this process (`clumpy splat_points` calls it when
+ * CLUMPY_DEVICES lists several devices): alpha == 1 && kernel_size == 1 takes the fast path of splat_points.cc:93-94,
+ * anything else is splat_disks.  Points are sharded by index range, every GPU counts its shard into a private
+ * accumulator, the GPU that owns a row band sums that band out of all accumulators through peer memory (NVLink),
+ * composites it and copies its rows back.  The result equals the one-GPU entry points' (the accumulators are sums). */
+int clumpy_cuda_splat_multi(const int* devices, int ndevices, const float* pts_host, uint32_t npts,
+                            uint32_t width, uint32_t height, uint8_t* img_host, float alpha,
+                            int kernel_size, int wrapx);
+
 /* ---- advect_points --------------------------------------------------------------------- */
 
 /* Host helper: the per-point reset offsets of commands/advect_points.cc:127-135
@@ -283,11 +292,16 @@ int clumpy_cuda_advect_finish_frame(clumpy_advect* adv);
  *   frames:   route_steps(count) / route_record(count, ...)
  *
  * `capacity` = point count of the largest shard (the same value on every rank).  Every rank must run the same
- * sequence of frame counts (groups are cut at the same frames everywhere). */
+ * sequence of frame counts (groups are cut at the same frames everywhere).
+ * route_begin allocates the inbox when *inbox_dev is NULL on entry and returns it with its size; the run frees it at
+ * advect_end.  With *inbox_dev != NULL it uses that memory (*inbox_bytes of it, from clumpy_cuda_dev_alloc or an
+ * earlier run's size) and leaves it to the caller: an application that runs the command repeatedly keeps one arena
+ * per GPU, and its peers' mappings of it, across runs (clumpy_b200/multigpu.py does). */
 #define CLUMPY_IPC_HANDLE_BYTES 64
 int clumpy_cuda_ipc_export(clumpy_cuda_ctx* ctx, const void* dptr, void* handle64);
 int clumpy_cuda_ipc_open(clumpy_cuda_ctx* ctx, const void* handle64, void** dptr);
 int clumpy_cuda_ipc_close(clumpy_cuda_ctx* ctx, void* dptr);
+int clumpy_cuda_advect_route_bytes(uint32_t capacity, int world, size_t* inbox_bytes); /* size of an inbox */
 int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int world, uint32_t capacity,
                                    void** inbox_dev, size_t* inbox_bytes);
 int clumpy_cuda_advect_route_peers(clumpy_advect* adv, void* const* peer_inbox);
