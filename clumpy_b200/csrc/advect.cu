@@ -375,6 +375,7 @@ static int advect_begin_impl(clumpy_advect* a, const clumpy_advect_desc& d) {
         const uint32_t nframes = a->nframes;
         offs_thread = std::thread([=] { age_offsets_host(nframes, n_in, offs_pinned); });
     }
+    trace_mark(ctx, "advect_begin: events, offsets thread started");
     struct Joiner { // whatever happens below, the thread is joined and the pinned buffer goes back to the cache
         std::thread& t; clumpy_cuda_ctx* c; uint32_t* p; size_t bytes;
         ~Joiner() { if (t.joinable()) t.join(); cudaStreamSynchronize(c->stream); ctx_pinned_put(c, p, bytes); }
@@ -386,6 +387,7 @@ static int advect_begin_impl(clumpy_advect* a, const clumpy_advect_desc& d) {
         a->vel_owned = false;
     } else {
         DEV_ALLOC(ctx, &a->vel, npix * 8);
+        trace_mark(ctx, "advect_begin: field allocated");
         CK(cudaMemcpyAsync(a->vel, d.vel, npix * 8, cudaMemcpyHostToDevice, ctx->stream));
         trace_mark(ctx, "advect_begin: field upload");
     }

@@ -47,23 +47,35 @@ int minmax_fetch(clumpy_cuda_ctx* ctx, float* minval, float* maxval) {
     return CLUMPY_OK;
 }
 
+// The cache remembers the size each buffer was allocated with; a request takes the smallest cached buffer that is
+// large enough but not more than 1.5x larger (a 64 MB buffer handed out for a 32 MB request would be missing when
+// the next 64 MB request comes, and pinning is what the cache exists to avoid).
 void* ctx_pinned_get(clumpy_cuda_ctx* ctx, size_t bytes) {
-    // smallest cached buffer that is large enough
     int best = -1;
-    for (int i = 0; i < (int)ctx->pinned_cache.size(); ++i)
-        if (ctx->pinned_cache[i].second >= bytes && (best < 0 || ctx->pinned_cache[i].second < ctx->pinned_cache[best].second)) best = i;
-    if (best >= 0) {
-        void* p = ctx->pinned_cache[best].first;
-        ctx->pinned_cache.erase(ctx->pinned_cache.begin() + best);
-        return p;
+    for (int i = 0; i < (int)ctx->pinned_cache.size(); ++i) {
+        const size_t have = ctx->pinned_cache[i].second;
+        if (have >= bytes && have <= bytes + bytes / 2 && (best < 0 || have < ctx->pinned_cache[best].second)) best = i;
     }
-    return clumpy_cuda_host_alloc(bytes);
+    void* p = nullptr;
+    size_t have = bytes;
+    if (best >= 0) {
+        p = ctx->pinned_cache[best].first;
+        have = ctx->pinned_cache[best].second;
+        ctx->pinned_cache.erase(ctx->pinned_cache.begin() + best);
+    } else {
+        p = clumpy_cuda_host_alloc(bytes);
+    }
+    if (p) ctx->pinned_out.emplace_back(p, have);
+    return p;
 }
 
-void ctx_pinned_put(clumpy_cuda_ctx* ctx, void* p, size_t bytes) {
+void ctx_pinned_put(clumpy_cuda_ctx* ctx, void* p, size_t /*bytes_requested*/) {
     if (!p) return;
-    if (ctx->pinned_cache.size() >= 16) { cudaFreeHost(p); return; }
-    ctx->pinned_cache.emplace_back(p, bytes);
+    size_t have = 0;
+    for (size_t i = 0; i < ctx->pinned_out.size(); ++i)
+        if (ctx->pinned_out[i].first == p) { have = ctx->pinned_out[i].second; ctx->pinned_out.erase(ctx->pinned_out.begin() + i); break; }
+    if (have == 0 || ctx->pinned_cache.size() >= 16) { cudaFreeHost(p); return; }
+    ctx->pinned_cache.emplace_back(p, have);
 }
 
 } // namespace clumpy

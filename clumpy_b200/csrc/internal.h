@@ -69,7 +69,8 @@ struct clumpy_cuda_ctx {
     uint32_t* h_minmax = nullptr; // pinned mirror
     // Pinned host buffers handed back by finished commands, kept for the next one (pinning 64 MB costs
     // ~40 ms, more than a whole 20-frame advect_points run at the C4 size); freed with the context.
-    std::vector<std::pair<void*, size_t>> pinned_cache;
+    std::vector<std::pair<void*, size_t>> pinned_cache; // free buffers and the size each was allocated with
+    std::vector<std::pair<void*, size_t>> pinned_out;   // buffers handed out
 };
 
 namespace clumpy {

@@ -229,3 +229,49 @@ def test_cli_advect_points_on_several_devices(golden, tmp_path):
     assert hashlib.md5(p.stdout).hexdigest() == golden["meta"]["c1_advect_stdout_md5"]
     got = [hashlib.md5(open(tmp_path / f"{i:03}anim.npy", "rb").read()).hexdigest() for i in range(240)]
     assert got == golden["meta"]["c1_frame_md5"]
+
+
+# ---- splat_points on several devices (last row) ----------------------------------------------------------
+
+def _test_devices(default):
+    env = os.environ.get("CLUMPY_TEST_DEVICES")
+    return [int(v) for v in env.split(",")] if env else default
+
+
+@pytest.mark.parametrize("k,alpha,wrap,n,w,h", [
+    (1, 1.0, False, 30000, 300, 200),     # the fast path of the command (stores 255)
+    (3, 1.0, False, 50000, 300, 201),     # dense: 32-bit counts summed across the devices
+    (5, 0.6, True, 30000, 257, 131),      # x-wrap
+    (3, 1.0, False, 2000, 300, 200),      # sparse: exact-order cells (count + sum of ORIGINAL indices)
+    (7, 0.3, True, 900, 400, 300),
+    (1, 0.5, False, 5000, 33, 17),        # fewer rows than some band splits like
+    (3, 1.0, False, 0, 64, 64),
+])
+def test_splat_multi_equals_one_device(ctx, k, alpha, wrap, n, w, h):
+    """clumpy_cuda_splat_multi: the accumulators of the devices sum to the one-device accumulator, so the image must
+    be IDENTICAL to clumpy_cuda_splat_points / _splat_disks (which the parity tests pin to the reference)."""
+    import clumpy_b200
+    rng = np.random.default_rng(k * 100 + n)
+    pts = ((rng.random((n, 2)) * 1.1 - 0.05) * [w, h]).astype(np.float32)
+    base = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    one = ctx.splat_points(pts, w, h, img=base) if (k == 1 and alpha == 1.0) else ctx.splat_disks(pts, w, h, alpha, k, wrapx=wrap, img=base)
+    for devices in (_test_devices([0, 0]), _test_devices([0, 0, 0]) + [0]):
+        got = clumpy_b200.splat_multi(devices, pts, w, h, alpha, k, wrapx=wrap, img=base)
+        assert np.array_equal(got, one), (devices, int(np.abs(got.astype(int) - one.astype(int)).max()))
+
+
+def test_cli_splat_points_on_several_devices(golden, tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spl, m = golden["splat"], golden["meta"]
+    np.save(tmp_path / "pts.npy", spl["pts"])
+    env = dict(os.environ, CLUMPY_DEVICES=os.environ.get("CLUMPY_TEST_DEVICES", "0,0"))
+    for name in ("k1_a1", "k3_a1", "k7_a1"):
+        c = m[f"splat_{name}"]
+        p = subprocess.run([os.path.join(root, "clumpy_b200", "clumpy"), "splat_points", "pts.npy", "96x64", "u8disk", str(c["k"]), str(c["alpha"]), f"{name}.npy"],
+                           cwd=tmp_path, env=env, capture_output=True)
+        assert p.returncode == 0 and p.stdout.decode().strip() == c["stdout"]
+        d = np.abs(np.load(tmp_path / f"{name}.npy").astype(int) - spl[name].astype(int))
+        assert d.max() <= 1 and (d <= 1).mean() >= 0.999, name
+        if c["k"] == 1:
+            assert d.max() == 0
