@@ -978,11 +978,14 @@ template <bool WRAP, bool SPLAT, typename OffT>
 static void launch_route_t(clumpy_advect* a, const RouteDev& rd) {
     const uint32_t grid = ceil_div(a->npts, ROUTE_BLOCK); // CTA c owns region c of its segments
     const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch, a->keep_pos ? 1 : 0, 0};
+    // CLUMPY_ROUTE_SMEM_KB=<n> (A/B): n KB of unused dynamic shared memory per CTA, to cap how many CTAs of this
+    // kernel an SM holds (227 KB / n) and leave room for the drain / composite launches of the side stream
+    const size_t pad = (size_t)std::min(std::max(env_int("CLUMPY_ROUTE_SMEM_KB", 0), 0), 48) * 1024;
     if (a->route.minb == 8)
-        advect_route_kernel<WRAP, SPLAT, OffT, 8><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
+        advect_route_kernel<WRAP, SPLAT, OffT, 8><<<grid, ADVECT_THREADS, pad, a->ctx->stream>>>(
             a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);
     else
-        advect_route_kernel<WRAP, SPLAT, OffT, 6><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
+        advect_route_kernel<WRAP, SPLAT, OffT, 6><<<grid, ADVECT_THREADS, pad, a->ctx->stream>>>(
             a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);
 }
 
@@ -1156,6 +1159,7 @@ static int route_group(clumpy_advect* adv, uint32_t nf, RecordSink* sink, RouteE
     rd.band_f16 = adv->cell_mode == CELL_F16 ? 1 : 0;
     rd.epoch = splat ? rt.epoch + 1u : rt.epoch;
     rd.loopback = rt.loopback ? 1 : 0;
+    rd.aggregate = (env_int("CLUMPY_CUDA_HINTS", 0) & 16) ? 1 : 0;
     rd.ticket = rt.ticket;
     for (int r = 0; r < rt.world; ++r) {
         rd.inbox[r] = rt.peer_inbox[r];

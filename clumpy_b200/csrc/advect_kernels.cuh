@@ -14,6 +14,8 @@
 #include "device_utils.cuh"
 #include "internal.h"
 
+#include <cuda_fp16.h>
+
 namespace clumpy {
 
 constexpr int ADVECT_THREADS = 256;
@@ -35,6 +37,20 @@ __device__ __forceinline__ void cell_add_f16(uint32_t* __restrict__ words, long 
     const uint32_t one = (cell & 1) ? 0x3C000000u : 0x00003C00u;
     asm volatile("red.global.add.noftz.f16x2 [%0], %1;" :: "l"(words + (cell >> 1)), "r"(one) : "memory");
 }
+// n counts at once (n <= 32: exact in a half)
+__device__ __forceinline__ void cell_add_f16_n(uint32_t* __restrict__ words, long long cell, uint32_t n) {
+    const uint32_t h = (uint32_t)__half_as_ushort(__uint2half_rn(n));
+    const uint32_t v = (cell & 1) ? (h << 16) : h;
+    asm volatile("red.global.add.noftz.f16x2 [%0], %1;" :: "l"(words + (cell >> 1)), "r"(v) : "memory");
+}
+// Warp-aggregated count: the lanes of the calling (converged) group that hit the same cell send ONE reduction.
+// Pays when the cloud has clumped (streamlines, points stalled just outside the image: all on a few cells);
+// costs a MATCH per call otherwise.  GeomDev.hints bit 4 (CLUMPY_CUDA_HINTS=16) switches it on (A/B).
+__device__ __forceinline__ void cell_add_f16_agg(uint32_t* __restrict__ words, long long cell) {
+    const uint32_t active = __activemask();
+    const uint32_t same = __match_any_sync(active, cell);
+    if ((uint32_t)(__ffs(same) - 1) == (threadIdx.x & 31u)) cell_add_f16_n(words, cell, (uint32_t)__popc(same));
+}
 __device__ __forceinline__ void cell_add_f16(uint32_t* __restrict__ words, long long cell, uint64_t pol) {
     const uint32_t one = (cell & 1) ? 0x3C000000u : 0x00003C00u;
     asm volatile("red.global.add.L2::cache_hint.noftz.f16x2 [%0], %1, %2;" :: "l"(words + (cell >> 1)), "r"(one), "l"(pol) : "memory");
@@ -55,7 +71,8 @@ __device__ __forceinline__ void count_point(uint32_t* __restrict__ hist, int32_t
     } else if (MODE == CELL_U32) {
         atomicAdd(hist + at, 1u);
     } else if (MODE == CELL_F16) {
-        cell_add_f16(hist, at, red_pol);
+        if (g.hints & 16) cell_add_f16_agg(hist, at);
+        else cell_add_f16(hist, at, red_pol);
         if (WRAP && g.halo > 0) {
             int32_t m = cx % g.width;
             if (m < 0) m += g.width;
@@ -177,6 +194,7 @@ struct RouteDev {
     uint32_t* flags[ROUTE_MAX_WORLD];   // rank r's epoch flags (peer-mapped): [source]
     uint32_t* band[ROUTE_MAX_FUSE];     // this rank's band buffer of frame f
     int band_f16;                       // band cells are half floats (else uint32)
+    int aggregate;                      // own-band counts are warp-aggregated (CLUMPY_CUDA_HINTS bit 4)
     int loopback;                       // profiling aid: every "peer" is this rank itself (see route_begin)
     uint32_t epoch;                     // epoch of the group
     uint32_t* ticket;                   // CTAs of this launch that are done
@@ -185,9 +203,10 @@ struct RouteDev {
 // One count into a band buffer.  Half cells in x-wrap mode (wrap_w = image width, else 0): the group
 // composite reads its halo columns as they are, so a cell within `halo` columns of the left / right edge is
 // also counted into the halo column on the other side (see count_point).
-__device__ __forceinline__ void band_add(uint32_t* __restrict__ band, uint32_t entry, int f16, int wrap_w, int halo, int pitch) {
+__device__ __forceinline__ void band_add(uint32_t* __restrict__ band, uint32_t entry, int f16, int wrap_w, int halo, int pitch, int agg = 0) {
     if (!f16) { atomicAdd(band + entry, 1u); return; }
-    cell_add_f16(band, (long long)entry);
+    if (agg) cell_add_f16_agg(band, (long long)entry);
+    else cell_add_f16(band, (long long)entry);
     if (wrap_w && halo > 0) {
         const int m = (int)(entry % (uint32_t)pitch) - halo;
         if (m >= wrap_w - halo) cell_add_f16(band, (long long)entry - wrap_w);
@@ -207,7 +226,7 @@ __device__ __forceinline__ void route_send(const RouteDev& rt, int f, uint32_t* 
 // within the sprite's reach of a band edge also go to the neighbouring band, whose composite needs them.
 __device__ __forceinline__ void route_cell(const RouteDev& rt, int f, uint32_t* cta_n, int owner, int r, uint32_t ux, int wrap_w) {
     const uint32_t entry = (uint32_t)((r + rt.halo) * rt.pitch) + ux; // band rows: [halo above | chunk | halo below]
-    if (owner == rt.me) band_add(rt.band[f], entry, rt.band_f16, wrap_w, rt.halo, rt.pitch);
+    if (owner == rt.me) band_add(rt.band[f], entry, rt.band_f16, wrap_w, rt.halo, rt.pitch, rt.aggregate);
     else route_send(rt, f, cta_n, owner, entry);
     if (r < rt.halo && owner > 0) {
         const uint32_t e = (uint32_t)((r + rt.chunk + rt.halo) * rt.pitch) + ux;

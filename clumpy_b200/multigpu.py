@@ -108,8 +108,8 @@ class BandPlan:
         """Image rows [y0, y1) whose pixels rank `rank` composites: those whose whole window of
         2*halo+1 padded rows lies in the rank's chunk plus its two halos."""
         lo, hi = self.padded_rows(rank)
-        y0, y1 = max(0, lo - self.halo), min(self.height, hi - self.halo)
-        return (y0, max(y0, y1))
+        y0, y1 = min(self.height, max(0, lo - self.halo)), min(self.height, hi - self.halo)
+        return (y0, max(y0, y1))  # (empty for a rank whose chunk lies wholly in the row padding)
 
     def band_buffer_rows(self):
         """Rows of the per-rank band buffer: halo above + chunk + halo below + tile slack."""
