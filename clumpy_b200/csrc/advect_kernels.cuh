@@ -243,9 +243,12 @@ __device__ __forceinline__ void route_cell(const RouteDev& rt, int f, uint32_t* 
 // The group fence, sender side.  Called by every CTA after a barrier that follows its last remote store:
 // thread 0's fence.sys is cumulative over the stores of the whole CTA (they happen-before it through the
 // barrier); the ticket orders the CTAs; the last one fences again and publishes.
-__device__ __forceinline__ void route_group_fence(const RouteDev& rt) {
+__device__ __forceinline__ void route_group_fence(const RouteDev& rt, bool cta_sent) {
     if (threadIdx.x != 0) return;
-    __threadfence_system();
+    // a CTA whose points all landed in this rank's own band has nothing to publish: its reductions are consumed
+    // by this rank's own later launches (stream order); the fence waits for acknowledgements from the peers and
+    // is worth skipping
+    if (cta_sent) __threadfence_system();
     const uint32_t done = atomicAdd(rt.ticket, 1u);
     if (done != gridDim.x - 1u) return;
     *rt.ticket = 0u; // for the next launch (launches of one rank are stream-ordered)
@@ -331,13 +334,14 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
     if (!SPLAT) return;
     __syncthreads(); // every entry of this CTA is written, cta_n is final
     // the non-zero counts go to their destinations (the receivers zero them again)
+    uint32_t n = 0u;
     if (threadIdx.x < (uint32_t)(rt.nf * ROUTE_MAX_WORLD)) {
         const int f = threadIdx.x / ROUTE_MAX_WORLD, d = threadIdx.x % ROUTE_MAX_WORLD;
-        const uint32_t n = d < rt.world ? cta_n[f][d] : 0u;
+        n = d < rt.world ? cta_n[f][d] : 0u;
         if (n) *reinterpret_cast<volatile uint32_t*>(rt.cnt[d] + rt.cnt_off + (size_t)f * rt.cnt_frame_stride + (size_t)rt.me * rt.nregion + blockIdx.x) = n;
     }
-    __syncthreads();
-    route_group_fence(rt);
+    const bool cta_sent = __syncthreads_or(n != 0u) != 0;
+    route_group_fence(rt, cta_sent);
 }
 
 // The same fence for a rank that has no points this run (no route kernel to carry it).

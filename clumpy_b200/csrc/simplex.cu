@@ -12,6 +12,8 @@
 #include "device_utils.cuh"
 #include "internal.h"
 
+#include <algorithm>
+
 namespace clumpy {
 
 constexpr int SIMPLEX_THREADS = 256;
@@ -84,45 +86,54 @@ __device__ __forceinline__ float simplex2(const uint8_t* __restrict__ perm, floa
 // Band rows [row0, row0 + nrows) of a `width`-wide image; out is nrows x width.
 struct PermArg { uint8_t p[256]; }; // passed by value: lands in the constant bank, no allocation
 
+// Pixel indexing shared by the two kernels: a CTA covers SIMPLEX_THREADS * SIMPLEX_PX consecutive pixels of ONE
+// row (blockIdx.x strides over the row, blockIdx.y over the rows), so no 64-bit division is needed per pixel
+// group (round 1 indexed a flat pixel range: ~15 of its ~215 instructions per pixel were that division).
+template <typename Eval>
+__device__ __forceinline__ void simplex_rows(uint32_t width, uint32_t nrows, float* __restrict__ out,
+                                             uint32_t* __restrict__ minmax, int vec_ok, Eval eval) {
+    float lo = 0.f, hi = 0.f;
+    bool any = false;
+    for (uint32_t row = blockIdx.y; row < nrows; row += gridDim.y) {
+        float* const orow = out + (size_t)row * width;
+        for (uint32_t col0 = (blockIdx.x * SIMPLEX_THREADS + threadIdx.x) * SIMPLEX_PX; col0 < width;
+             col0 += gridDim.x * SIMPLEX_THREADS * SIMPLEX_PX) {
+            float vals[SIMPLEX_PX];
+            const int n = (width - col0 < (uint32_t)SIMPLEX_PX) ? (int)(width - col0) : SIMPLEX_PX;
+#pragma unroll
+            for (int k = 0; k < SIMPLEX_PX; ++k) {
+                if (k < n) {
+                    const float s = eval(col0 + (uint32_t)k, row);
+                    vals[k] = s;
+                    if (!any) { lo = hi = s; any = true; }
+                    else { lo = (s < lo) ? s : lo; hi = (hi < s) ? s : hi; }
+                }
+            }
+            if (vec_ok && n == SIMPLEX_PX) {
+                *reinterpret_cast<float4*>(orow + col0) = make_float4(vals[0], vals[1], vals[2], vals[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < SIMPLEX_PX; ++k)
+                    if (k < n) orow[col0 + k] = vals[k];
+            }
+        }
+    }
+    block_minmax_commit(lo, any, hi, any, minmax);
+}
+
 __global__ void __launch_bounds__(SIMPLEX_THREADS)
-simplex_kernel(const PermArg perm_arg, uint32_t width, uint32_t row0, uint64_t npix,
+simplex_kernel(const PermArg perm_arg, uint32_t width, uint32_t row0, uint32_t nrows,
                float step, float scale, float* __restrict__ out, uint32_t* __restrict__ minmax,
                int vec_ok) {
     __shared__ uint8_t perm[256];
     perm[threadIdx.x] = perm_arg.p[threadIdx.x]; // blockDim.x == 256
     __syncthreads();
-
-    float lo = 0.f, hi = 0.f;
-    bool any = false;
-    const uint64_t chunk = (uint64_t)SIMPLEX_THREADS * SIMPLEX_PX;
-    for (uint64_t base = (uint64_t)blockIdx.x * chunk + (uint64_t)threadIdx.x * SIMPLEX_PX;
-         base < npix; base += (uint64_t)gridDim.x * chunk) {
-        uint32_t row = (uint32_t)(base / width);
-        uint32_t col = (uint32_t)(base - (uint64_t)row * width);
-        float vals[SIMPLEX_PX];
-        const int n = (npix - base < SIMPLEX_PX) ? (int)(npix - base) : SIMPLEX_PX;
-#pragma unroll
-        for (int k = 0; k < SIMPLEX_PX; ++k) {
-            if (k < n) {
-                // generate_simplex.cc:75-77: FP32 product step*index, then amplitude * noise / 47
-                const float uf = __fmul_rn(step, (float)col);
-                const float vf = __fmul_rn(step, (float)(row0 + row));
-                const float s = simplex2(perm, uf, vf) * scale;
-                vals[k] = s;
-                if (!any) { lo = hi = s; any = true; }
-                else { lo = (s < lo) ? s : lo; hi = (hi < s) ? s : hi; }
-                if (++col == width) { col = 0; ++row; }
-            }
-        }
-        if (vec_ok && n == SIMPLEX_PX) {
-            *reinterpret_cast<float4*>(out + base) = make_float4(vals[0], vals[1], vals[2], vals[3]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < SIMPLEX_PX; ++k)
-                if (k < n) out[base + k] = vals[k];
-        }
-    }
-    block_minmax_commit(lo, any, hi, any, minmax);
+    simplex_rows(width, nrows, out, minmax, vec_ok, [&](uint32_t col, uint32_t row) {
+        // generate_simplex.cc:75-77: FP32 product step*index, then amplitude * noise / 47
+        const float uf = __fmul_rn(step, (float)col);
+        const float vf = __fmul_rn(step, (float)(row0 + row));
+        return simplex2(perm, uf, vf) * scale;
+    });
 }
 
 // Several octaves in one pass (README.md:28-36, extras/test.py:18-21: the reference runs generate_simplex once
@@ -135,46 +146,28 @@ struct OctavePerms { uint8_t p[SIMPLEX_MAX_OCTAVES][256]; };
 struct OctaveArgs { int n; float step[SIMPLEX_MAX_OCTAVES]; float scale[SIMPLEX_MAX_OCTAVES]; };
 
 __global__ void __launch_bounds__(SIMPLEX_THREADS)
-simplex_octaves_kernel(const OctavePerms perms_arg, const OctaveArgs oa, uint32_t width, uint32_t row0, uint64_t npix,
+simplex_octaves_kernel(const OctavePerms perms_arg, const OctaveArgs oa, uint32_t width, uint32_t row0, uint32_t nrows,
                        float* __restrict__ out, uint32_t* __restrict__ minmax, int vec_ok) {
     __shared__ uint8_t perm[SIMPLEX_MAX_OCTAVES][256];
     for (int o = 0; o < oa.n; ++o) perm[o][threadIdx.x] = perms_arg.p[o][threadIdx.x]; // blockDim.x == 256
     __syncthreads();
+    simplex_rows(width, nrows, out, minmax, vec_ok, [&](uint32_t col, uint32_t row) {
+        float total = 0.f;
+        for (int o = 0; o < oa.n; ++o) {
+            const float uf = __fmul_rn(oa.step[o], (float)col);
+            const float vf = __fmul_rn(oa.step[o], (float)(row0 + row));
+            const float s = simplex2(perm[o], uf, vf) * oa.scale[o];
+            total = o == 0 ? s : __fadd_rn(total, s);
+        }
+        return total;
+    });
+}
 
-    float lo = 0.f, hi = 0.f;
-    bool any = false;
-    const uint64_t chunk = (uint64_t)SIMPLEX_THREADS * SIMPLEX_PX;
-    for (uint64_t base = (uint64_t)blockIdx.x * chunk + (uint64_t)threadIdx.x * SIMPLEX_PX;
-         base < npix; base += (uint64_t)gridDim.x * chunk) {
-        uint32_t row = (uint32_t)(base / width);
-        uint32_t col = (uint32_t)(base - (uint64_t)row * width);
-        float vals[SIMPLEX_PX];
-        const int n = (npix - base < SIMPLEX_PX) ? (int)(npix - base) : SIMPLEX_PX;
-#pragma unroll
-        for (int k = 0; k < SIMPLEX_PX; ++k) {
-            if (k < n) {
-                float total = 0.f;
-                for (int o = 0; o < oa.n; ++o) {
-                    const float uf = __fmul_rn(oa.step[o], (float)col);
-                    const float vf = __fmul_rn(oa.step[o], (float)(row0 + row));
-                    const float s = simplex2(perm[o], uf, vf) * oa.scale[o];
-                    total = o == 0 ? s : __fadd_rn(total, s);
-                }
-                vals[k] = total;
-                if (!any) { lo = hi = total; any = true; }
-                else { lo = (total < lo) ? total : lo; hi = (hi < total) ? total : hi; }
-                if (++col == width) { col = 0; ++row; }
-            }
-        }
-        if (vec_ok && n == SIMPLEX_PX) {
-            *reinterpret_cast<float4*>(out + base) = make_float4(vals[0], vals[1], vals[2], vals[3]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < SIMPLEX_PX; ++k)
-                if (k < n) out[base + k] = vals[k];
-        }
-    }
-    block_minmax_commit(lo, any, hi, any, minmax);
+// A grid for simplex_rows: the row's pixel groups along x, as many rows along y as fill a few waves.
+static dim3 simplex_grid(const clumpy_cuda_ctx* ctx, uint32_t width, uint32_t nrows) {
+    const uint32_t gx = std::max<uint32_t>(1u, ceil_div(width, SIMPLEX_THREADS * SIMPLEX_PX));
+    const uint32_t want_y = std::max<uint32_t>(1u, ((uint32_t)ctx->sm_count * 8 * 4 + gx - 1) / gx);
+    return dim3(gx, std::min<uint32_t>(std::min<uint32_t>(nrows, want_y), 65535u));
 }
 
 static int run_simplex(clumpy_cuda_ctx* ctx, uint32_t width, uint32_t height, uint32_t row0,
@@ -187,17 +180,12 @@ static int run_simplex(clumpy_cuda_ctx* ctx, uint32_t width, uint32_t height, ui
     // generate_simplex.cc:59-67: float step from a double divide by the shorter side
     const float step = (width > height) ? (float)(frequency / height) : (float)(frequency / width);
     const float scale = (float)(amplitude / 47.0);
-    const uint64_t npix = (uint64_t)nrows * width;
     int rc = minmax_reset(ctx);
     if (rc) return rc;
-    if (npix > 0) {
-        const uint64_t chunk = (uint64_t)SIMPLEX_THREADS * SIMPLEX_PX;
-        uint64_t want = (npix + chunk - 1) / chunk;
-        uint64_t cap = (uint64_t)ctx->sm_count * 8 * 4; // a few waves of resident CTAs
-        uint32_t grid = (uint32_t)(want < cap ? want : cap);
-        const int vec_ok = ((uintptr_t)d_out % 16 == 0) ? 1 : 0;
-        simplex_kernel<<<grid, SIMPLEX_THREADS, 0, ctx->stream>>>(perm8, width, row0, npix, step,
-                                                                  scale, d_out, ctx->d_minmax, vec_ok);
+    if (nrows > 0) {
+        const int vec_ok = ((uintptr_t)d_out % 16 == 0 && width % 4 == 0) ? 1 : 0;
+        simplex_kernel<<<simplex_grid(ctx, width, nrows), SIMPLEX_THREADS, 0, ctx->stream>>>(perm8, width, row0, nrows, step,
+                                                                                              scale, d_out, ctx->d_minmax, vec_ok);
         CK_LAUNCH(ctx);
     }
     if (minval || maxval) return minmax_fetch(ctx, minval, maxval);
@@ -261,15 +249,12 @@ CLUMPY_API int clumpy_cuda_generate_simplex_octaves_dev(clumpy_cuda_ctx* ctx, ui
         oa.step[o] = (width > height) ? (float)(frequencies[o] / height) : (float)(frequencies[o] / width);
         oa.scale[o] = (float)(amplitudes[o] / 47.0);
     }
-    const uint64_t npix = (uint64_t)nrows * width;
     int rc = minmax_reset(ctx);
     if (rc) return rc;
-    if (npix > 0) {
-        const uint64_t chunk = (uint64_t)SIMPLEX_THREADS * SIMPLEX_PX;
-        const uint64_t want = (npix + chunk - 1) / chunk, cap = (uint64_t)ctx->sm_count * 8 * 4;
-        const int vec_ok = ((uintptr_t)out_dev % 16 == 0) ? 1 : 0;
-        simplex_octaves_kernel<<<(uint32_t)(want < cap ? want : cap), SIMPLEX_THREADS, 0, ctx->stream>>>(
-            perms, oa, width, row0, npix, out_dev, ctx->d_minmax, vec_ok);
+    if (nrows > 0) {
+        const int vec_ok = ((uintptr_t)out_dev % 16 == 0 && width % 4 == 0) ? 1 : 0;
+        simplex_octaves_kernel<<<simplex_grid(ctx, width, nrows), SIMPLEX_THREADS, 0, ctx->stream>>>(
+            perms, oa, width, row0, nrows, out_dev, ctx->d_minmax, vec_ok);
         CK_LAUNCH(ctx);
     }
     if (minval || maxval) return minmax_fetch(ctx, minval, maxval);

@@ -97,6 +97,14 @@ def generate_simplex(width, height, amplitude, frequency, seed):
     return out, lo.value, hi.value
 
 
+def generate_simplex_rows(width, height, row0, nrows, amplitude, frequency, seed):
+    """Rows [row0, row0 + nrows) of generate_simplex's (H, W) image -> (nrows, W) float32, min, max."""
+    out = np.empty((nrows, width), np.float32)
+    lib().oracle_generate_simplex_rows(width, height, row0, nrows, C.c_double(amplitude), C.c_double(frequency),
+                                       C.c_int64(int(seed)), _ptr(out, _f32p))
+    return out, float(out.min()) if out.size else 0.0, float(out.max()) if out.size else 0.0
+
+
 def curl_2d(src):
     """(H, W) float32 -> (H, W, 2) float32, min, max   [curl_2d.cc:29-77]"""
     src = _f32(src)

@@ -169,6 +169,23 @@ ORACLE_API void oracle_generate_simplex(uint32_t width, uint32_t height, double 
     if (maxval) *maxval = hi;
 }
 
+/* Rows [row0, row0 + nrows) of the same image (the band a GPU of a row-sharded run computes; also what lets a
+ * check at 16384 x 16384 look at a few rows without evaluating 268 M pixels on the CPU). */
+ORACLE_API void oracle_generate_simplex_rows(uint32_t width, uint32_t height, uint32_t row0, uint32_t nrows,
+                                             double amplitude, double frequency, int64_t seed, float* out)
+{
+    int16_t perm[256];
+    oracle_simplex_perm(seed, perm);
+    float step = (width > height) ? (float)(frequency / height) : (float)(frequency / width);
+    for (uint32_t r = 0; r < nrows; ++r) {
+        for (int col = 0; col < (int)width; ++col) {
+            double u = (double)(step * (float)col);
+            double v = (double)(step * (float)(int)(row0 + r));
+            out[(size_t)r * width + col] = (float)(amplitude * oracle_simplex2(perm, u, v));
+        }
+    }
+}
+
 /* =============================================================================================
  * curl_2d
  * ========================================================================================== */

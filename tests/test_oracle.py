@@ -204,3 +204,17 @@ def test_producers_against_the_compiled_reference(oracle_mod, tmp_path):
     for (w, h, fr, sx, sy) in [(500, 500, 0.01, 1.0, 5.0), (77, 200, 1.5, 0.1, 9.0)]:
         run("pendulum_phase", f"{w}x{h}", str(fr), str(sx), str(sy), "f.npy")
         assert np.array_equal(_bits(np.load(tmp_path / "f.npy")), _bits(oracle_mod.pendulum_phase(w, h, fr, sx, sy)))
+
+
+def test_simplex_rows_equal_the_whole_image_and_the_reference_corner(oracle_mod, golden):
+    """The row-band entry of the restatement (used for checks at 16384 x 16384) equals the whole-image one, and
+    the 4-octave sum of its rows equals the corner of the reference's own 16384 x 16384 octaves (summed in FP32)."""
+    whole, _, _ = oracle_mod.generate_simplex(300, 200, 1.5, 12.0, 3)
+    rows, _, _ = oracle_mod.generate_simplex_rows(300, 200, 37, 50, 1.5, 12.0, 3)
+    assert np.array_equal(rows.view(np.uint32), whole[37:87].view(np.uint32))
+    corner = golden["c3_corner"]
+    total = None
+    for amp, freq, seed in golden["meta"]["c3_octaves"]:
+        o, _, _ = oracle_mod.generate_simplex_rows(16384, 16384, 0, corner.shape[0], amp, freq, int(seed))
+        total = o if total is None else (total + o).astype(np.float32)
+    assert np.array_equal(total[:, :corner.shape[1]].view(np.uint32), corner.view(np.uint32))

@@ -34,7 +34,7 @@ if os.environ.get("ROUTED_SINGLE_PLAIN") == "1":  # the single-GPU kernels on th
     print(f"plain advect, {len(pts)} points: advect / composite ms per launch, frames per launch: {adv.profile_stages(12, serial=True)}")
     adv.close(); ctx.close(); dist.destroy_process_group(); sys.exit(0)
 run = RoutedAdvect(ctx, pts, vel, cfg["step_size"], cfg["kernel_size"], cfg["decay"], cfg["nframes"], dist, dev)
-run.step(80); torch.cuda.synchronize()
+run.step(int(os.environ.get("ROUTED_SINGLE_WARM", "80"))); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(stream); run.step(steps); e1.record(stream); torch.cuda.synchronize()
 print(f"routed single rank, {len(pts)} points on {w}x{h}: {e0.elapsed_time(e1)/steps:.4f} ms/frame; "
