@@ -974,7 +974,7 @@ static uint32_t* route_band(const clumpy_advect* adv, int set, int f) {
     return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(adv->route.band) + (size_t)(set * ROUTE_MAX_FUSE + f) * adv->route.band_bytes);
 }
 
-template <bool WRAP, bool SPLAT, typename OffT>
+template <bool WRAP, bool SPLAT, bool F16, typename OffT>
 static void launch_route_t(clumpy_advect* a, const RouteDev& rd) {
     const uint32_t grid = ceil_div(a->npts, ROUTE_BLOCK); // CTA c owns region c of its segments
     const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch, a->keep_pos ? 1 : 0, 0};
@@ -982,10 +982,10 @@ static void launch_route_t(clumpy_advect* a, const RouteDev& rd) {
     // kernel an SM holds (227 KB / n) and leave room for the drain / composite launches of the side stream
     const size_t pad = (size_t)std::min(std::max(env_int("CLUMPY_ROUTE_SMEM_KB", 0), 0), 48) * 1024;
     if (a->route.minb == 8)
-        advect_route_kernel<WRAP, SPLAT, OffT, 8><<<grid, ADVECT_THREADS, pad, a->ctx->stream>>>(
+        advect_route_kernel<WRAP, SPLAT, F16, OffT, 8><<<grid, ADVECT_THREADS, pad, a->ctx->stream>>>(
             a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);
     else
-        advect_route_kernel<WRAP, SPLAT, OffT, 6><<<grid, ADVECT_THREADS, pad, a->ctx->stream>>>(
+        advect_route_kernel<WRAP, SPLAT, F16, OffT, 6><<<grid, ADVECT_THREADS, pad, a->ctx->stream>>>(
             a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);
 }
 
@@ -1066,13 +1066,15 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     // the (zero) framebuffer as it is; the route kernels are loaded without being run.
     {
         cudaFuncAttributes fa;
-#define ROUTE_LOAD(W, S) CK(adv->off16 ? (rt.minb == 8 ? cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, uint16_t, 8>) \
-                                                        : cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, uint16_t, 6>)) \
-                                       : (rt.minb == 8 ? cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, uint32_t, 8>) \
-                                                        : cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, uint32_t, 6>)))
+#define ROUTE_LOAD2(W, S, F) CK(adv->off16 ? (rt.minb == 8 ? cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, F, uint16_t, 8>) \
+                                                           : cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, F, uint16_t, 6>)) \
+                                          : (rt.minb == 8 ? cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, F, uint32_t, 8>) \
+                                                           : cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, F, uint32_t, 6>)))
+#define ROUTE_LOAD(W, S) do { if (adv->cell_mode == CELL_F16) ROUTE_LOAD2(W, S, true); else ROUTE_LOAD2(W, S, false); } while (0)
         if (adv->wrapx) { ROUTE_LOAD(true, true); ROUTE_LOAD(true, false); }
         else            { ROUTE_LOAD(false, true); ROUTE_LOAD(false, false); }
 #undef ROUTE_LOAD
+#undef ROUTE_LOAD2
         CK(cudaFuncGetAttributes(&fa, route_signal_kernel));
         DrainDev dd = {};
         dd.inbox = rt.inbox; dd.cnt = rt.inbox + rt.cnt_offset;
@@ -1159,7 +1161,6 @@ static int route_group(clumpy_advect* adv, uint32_t nf, RecordSink* sink, RouteE
     rd.band_f16 = adv->cell_mode == CELL_F16 ? 1 : 0;
     rd.epoch = splat ? rt.epoch + 1u : rt.epoch;
     rd.loopback = rt.loopback ? 1 : 0;
-    rd.aggregate = (env_int("CLUMPY_CUDA_HINTS", 0) & 16) ? 1 : 0;
     rd.ticket = rt.ticket;
     for (int r = 0; r < rt.world; ++r) {
         rd.inbox[r] = rt.peer_inbox[r];
@@ -1168,7 +1169,8 @@ static int route_group(clumpy_advect* adv, uint32_t nf, RecordSink* sink, RouteE
     }
     if (ev) CK(cudaEventRecord(ev->r0, main_stream));
     if (adv->npts) {
-#define ROUTE_LAUNCH(W, S) (adv->off16 ? launch_route_t<W, S, uint16_t>(adv, rd) : launch_route_t<W, S, uint32_t>(adv, rd))
+#define ROUTE_LAUNCH(W, S) (adv->cell_mode == CELL_F16 ? (adv->off16 ? launch_route_t<W, S, true, uint16_t>(adv, rd) : launch_route_t<W, S, true, uint32_t>(adv, rd)) \
+                                                       : (adv->off16 ? launch_route_t<W, S, false, uint16_t>(adv, rd) : launch_route_t<W, S, false, uint32_t>(adv, rd)))
         if (adv->wrapx) { if (splat) ROUTE_LAUNCH(true, true); else ROUTE_LAUNCH(true, false); }
         else            { if (splat) ROUTE_LAUNCH(false, true); else ROUTE_LAUNCH(false, false); }
 #undef ROUTE_LAUNCH
@@ -1199,7 +1201,8 @@ static int route_group(clumpy_advect* adv, uint32_t nf, RecordSink* sink, RouteE
         dd.wrap_w = adv->wrapx ? (int)adv->width : 0; dd.halo = adv->geom.halo; dd.pitch = adv->geom.pitch;
         // A small grid: these CTAs may sit waiting for a peer's epoch while route kernels run on the
         // main stream, and must leave them most of the SMs.
-        const uint32_t dgrid = std::min<uint32_t>(256u, std::max<uint32_t>(1u, ceil_div((uint32_t)rt.cnt_per_frame, 8u))); // a warp per region and frame
+        // 16 (frame, region) pairs per warp; the CTAs wait (one thread each) for the peers' epochs before they work
+        const uint32_t dgrid = std::min<uint32_t>((uint32_t)ctx->sm_count * 8u, std::max<uint32_t>(1u, ceil_div((uint32_t)(nf * rt.cnt_per_frame), 16u * 8u)));
         if (adv->cell_mode == CELL_F16) drain_group_kernel<CELL_F16><<<dgrid, 256, 0, side>>>(dd);
         else drain_group_kernel<CELL_U32><<<dgrid, 256, 0, side>>>(dd);
         CK_LAUNCH(ctx);

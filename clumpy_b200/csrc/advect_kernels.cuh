@@ -37,20 +37,9 @@ __device__ __forceinline__ void cell_add_f16(uint32_t* __restrict__ words, long 
     const uint32_t one = (cell & 1) ? 0x3C000000u : 0x00003C00u;
     asm volatile("red.global.add.noftz.f16x2 [%0], %1;" :: "l"(words + (cell >> 1)), "r"(one) : "memory");
 }
-// n counts at once (n <= 32: exact in a half)
-__device__ __forceinline__ void cell_add_f16_n(uint32_t* __restrict__ words, long long cell, uint32_t n) {
-    const uint32_t h = (uint32_t)__half_as_ushort(__uint2half_rn(n));
-    const uint32_t v = (cell & 1) ? (h << 16) : h;
-    asm volatile("red.global.add.noftz.f16x2 [%0], %1;" :: "l"(words + (cell >> 1)), "r"(v) : "memory");
-}
-// Warp-aggregated count: the lanes of the calling (converged) group that hit the same cell send ONE reduction.
-// Pays when the cloud has clumped (streamlines, points stalled just outside the image: all on a few cells);
-// costs a MATCH per call otherwise.  GeomDev.hints bit 4 (CLUMPY_CUDA_HINTS=16) switches it on (A/B).
-__device__ __forceinline__ void cell_add_f16_agg(uint32_t* __restrict__ words, long long cell) {
-    const uint32_t active = __activemask();
-    const uint32_t same = __match_any_sync(active, cell);
-    if ((uint32_t)(__ffs(same) - 1) == (threadIdx.x & 31u)) cell_add_f16_n(words, cell, (uint32_t)__popc(same));
-}
+// (Warp-aggregated counts -- the lanes of a warp that hit the same cell sending ONE reduction, found with
+// match.any -- were measured in round 2 and lose: 0.0273 vs 0.0165 ms per frame for the route kernel at 2.1 M points,
+// profiles/r2_sweep_multi_2gpu_quarter.txt.  At 0.5 points per texel almost every lane has a cell of its own.)
 __device__ __forceinline__ void cell_add_f16(uint32_t* __restrict__ words, long long cell, uint64_t pol) {
     const uint32_t one = (cell & 1) ? 0x3C000000u : 0x00003C00u;
     asm volatile("red.global.add.L2::cache_hint.noftz.f16x2 [%0], %1, %2;" :: "l"(words + (cell >> 1)), "r"(one), "l"(pol) : "memory");
@@ -71,8 +60,7 @@ __device__ __forceinline__ void count_point(uint32_t* __restrict__ hist, int32_t
     } else if (MODE == CELL_U32) {
         atomicAdd(hist + at, 1u);
     } else if (MODE == CELL_F16) {
-        if (g.hints & 16) cell_add_f16_agg(hist, at);
-        else cell_add_f16(hist, at, red_pol);
+        cell_add_f16(hist, at, red_pol);
         if (WRAP && g.halo > 0) {
             int32_t m = cx % g.width;
             if (m < 0) m += g.width;
@@ -194,7 +182,6 @@ struct RouteDev {
     uint32_t* flags[ROUTE_MAX_WORLD];   // rank r's epoch flags (peer-mapped): [source]
     uint32_t* band[ROUTE_MAX_FUSE];     // this rank's band buffer of frame f
     int band_f16;                       // band cells are half floats (else uint32)
-    int aggregate;                      // own-band counts are warp-aggregated (CLUMPY_CUDA_HINTS bit 4)
     int loopback;                       // profiling aid: every "peer" is this rank itself (see route_begin)
     uint32_t epoch;                     // epoch of the group
     uint32_t* ticket;                   // CTAs of this launch that are done
@@ -203,10 +190,9 @@ struct RouteDev {
 // One count into a band buffer.  Half cells in x-wrap mode (wrap_w = image width, else 0): the group
 // composite reads its halo columns as they are, so a cell within `halo` columns of the left / right edge is
 // also counted into the halo column on the other side (see count_point).
-__device__ __forceinline__ void band_add(uint32_t* __restrict__ band, uint32_t entry, int f16, int wrap_w, int halo, int pitch, int agg = 0) {
+__device__ __forceinline__ void band_add(uint32_t* __restrict__ band, uint32_t entry, int f16, int wrap_w, int halo, int pitch) {
     if (!f16) { atomicAdd(band + entry, 1u); return; }
-    if (agg) cell_add_f16_agg(band, (long long)entry);
-    else cell_add_f16(band, (long long)entry);
+    cell_add_f16(band, (long long)entry);
     if (wrap_w && halo > 0) {
         const int m = (int)(entry % (uint32_t)pitch) - halo;
         if (m >= wrap_w - halo) cell_add_f16(band, (long long)entry - wrap_w);
@@ -226,7 +212,7 @@ __device__ __forceinline__ void route_send(const RouteDev& rt, int f, uint32_t* 
 // within the sprite's reach of a band edge also go to the neighbouring band, whose composite needs them.
 __device__ __forceinline__ void route_cell(const RouteDev& rt, int f, uint32_t* cta_n, int owner, int r, uint32_t ux, int wrap_w) {
     const uint32_t entry = (uint32_t)((r + rt.halo) * rt.pitch) + ux; // band rows: [halo above | chunk | halo below]
-    if (owner == rt.me) band_add(rt.band[f], entry, rt.band_f16, wrap_w, rt.halo, rt.pitch, rt.aggregate);
+    if (owner == rt.me) band_add(rt.band[f], entry, rt.band_f16, wrap_w, rt.halo, rt.pitch);
     else route_send(rt, f, cta_n, owner, entry);
     if (r < rt.halo && owner > 0) {
         const uint32_t e = (uint32_t)((r + rt.chunk + rt.halo) * rt.pitch) + ux;
@@ -259,7 +245,7 @@ __device__ __forceinline__ void route_group_fence(const RouteDev& rt, bool cta_s
     }
 }
 
-template <bool WRAP, bool SPLAT, typename OffT, int MINB>
+template <bool WRAP, bool SPLAT, bool F16, typename OffT, int MINB>
 __global__ void __launch_bounds__(ADVECT_THREADS, MINB)
 advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                     const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
@@ -287,13 +273,22 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
             off[k] = ld_stream_off(offset + i, pol);
         }
     }
+    // each position is truncated once: the integers serve the splat of the frame that produced the position
+    // (splat_points.cc:143-144) and the velocity fetch of the next frame (advect_points.cc:23-37)
+    int32_t tx[ADVECT_PTS], ty[ADVECT_PTS];
+#pragma unroll
+    for (int k = 0; k < ADVECT_PTS; ++k) { tx[k] = __float2int_rz(p[k].x); ty[k] = __float2int_rz(p[k].y); }
+    // the rows of this rank's band that are out of the sprite's reach of its edges: a point that lands there
+    // (most do) costs one reduction and none of the routing logic
+    const uint32_t interior = (uint32_t)max(rt.chunk - 2 * rt.halo, 0);
+    const uint32_t padded_w = (uint32_t)(g.width + 2 * g.halo), padded_h = (uint32_t)(g.height + 2 * g.halo);
     uint32_t phase = rt.phase0;
     for (int f = 0; f < rt.nf; ++f) {
         float2 v[ADVECT_PTS];
 #pragma unroll
         for (int k = 0; k < ADVECT_PTS; ++k) { // nearest-texel fetch (advect_points.cc:23-37)
-            uint32_t x = f2u32_x86(p[k].x);
-            const uint32_t y = f2u32_x86(p[k].y);
+            uint32_t x = fetch_index(tx[k], p[k].x);
+            const uint32_t y = fetch_index(ty[k], p[k].y);
             if (WRAP) x = (width + (x % width)) % width;
             v[k] = make_float2(0.f, 0.f);
             if (live[k] && x < width && y < height) v[k] = __ldg(vel + ((size_t)y * width + x));
@@ -303,14 +298,17 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
             // pt += step * v: rounded multiply, then rounded add (:146)
             p[k] = make_float2(__fadd_rn(p[k].x, __fmul_rn(step, v[k].x)), __fadd_rn(p[k].y, __fmul_rn(step, v[k].y)));
             if (off[k] == phase) p[k] = orig[base + k * ADVECT_THREADS]; // reset AFTER the move (:147-152,166-170)
+            tx[k] = __float2int_rz(p[k].x);
+            ty[k] = __float2int_rz(p[k].y);
         }
         phase = phase + 1u == rt.nframes ? 0u : phase + 1u;
+        uint32_t* const band = rt.band[f];
 #pragma unroll
         for (int k = 0; SPLAT && k < ADVECT_PTS; ++k) {
             // splat_points.cc:143-144: centre texel by (int32_t) truncation; same tests as hist_index
-            const int32_t cx = f2i32_x86(p[k].x), cy = f2i32_x86(p[k].y);
+            const int32_t cx = splat_index(tx[k], p[k].x), cy = splat_index(ty[k], p[k].y);
             const uint32_t uy = (uint32_t)cy + (uint32_t)g.halo;
-            if (!live[k] || uy >= (uint32_t)(g.height + 2 * g.halo)) continue;
+            if (!live[k] || uy >= padded_h) continue;
             uint32_t ux;
             if (WRAP) {
                 int32_t m = cx % g.width;
@@ -318,9 +316,16 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                 ux = (uint32_t)(m + g.halo);
             } else {
                 ux = (uint32_t)cx + (uint32_t)g.halo;
-                if (ux >= (uint32_t)(g.width + 2 * g.halo)) continue;
+                if (ux >= padded_w) continue;
             }
-            int r = (int)uy - my_lo, owner = rt.me;
+            int r = (int)uy - my_lo;
+            if (!WRAP && (uint32_t)(r - rt.halo) < interior) { // own band, away from its edges
+                const uint32_t entry = (uint32_t)((r + rt.halo) * rt.pitch) + ux;
+                if (F16) cell_add_f16(band, (long long)entry);
+                else atomicAdd(band + entry, 1u);
+                continue;
+            }
+            int owner = rt.me;
             if ((uint32_t)r >= (uint32_t)rt.chunk) {
                 owner = min((int)(uy / (uint32_t)rt.chunk), rt.world - 1);
                 r = (int)uy - owner * rt.chunk;
@@ -404,40 +409,39 @@ drain_group_kernel(DrainDev d) {
         __syncthreads();
         if (!arrived) return;
     }
-    // The regions of a frame are dealt to the warps ROUND-ROBIN (region c goes to warp c % nwarp): the non-empty
-    // ones are the CTAs near a band edge, which are neighbours in region order, so a contiguous deal would leave
-    // all the work to a few warps.  A warp loads the count words of up to 32 of its regions in one go (most are
-    // zero: far CTAs send nothing), then works through the non-empty ones.
+    // The (frame, region) pairs of the group are dealt to the warps ROUND-ROBIN (pair p goes to warp p % nwarp): the
+    // non-empty regions are the CTAs near a band edge, which are neighbours in region order, so a contiguous deal
+    // would leave all the work to a few warps.  A warp loads the count words of up to 32 of its pairs in one go
+    // (most are zero: far CTAs send nothing), then works through the non-empty ones.
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarp = gridDim.x * (blockDim.x >> 5);
     const uint32_t per_frame = (uint32_t)d.world * d.nregion; // the count words of a frame are contiguous
-    for (int f = 0; f < d.nf; ++f) {
-        uint32_t* cnt = d.cnt + (size_t)f * d.cnt_frame_stride;
-        const uint32_t* inbox = d.inbox + (size_t)f * d.inbox_frame_stride;
-        uint32_t* band = d.band[f];
-        for (uint32_t k0 = 0; warp + k0 * nwarp < per_frame; k0 += 32u) {
-            const uint32_t c = warp + (k0 + lane) * nwarp;
-            uint32_t* word = cnt + c;
-            const uint32_t mine = (c < per_frame) ? min(__ldcg(word), ROUTE_REGION) : 0u; // written by a peer: read at L2
-            if (mine) *word = 0u;
-            uint32_t todo = __ballot_sync(0xFFFFFFFFu, mine != 0u);
-            while (todo) {
-                const int r = __ffs(todo) - 1;
-                todo &= todo - 1u;
-                const uint32_t n = __shfl_sync(0xFFFFFFFFu, mine, r);
-                const uint32_t* seg = inbox + (size_t)(warp + (k0 + (uint32_t)r) * nwarp) * ROUTE_REGION;
-                for (uint32_t i0 = 0; i0 < n; i0 += 256u) { // 8 loads in flight per lane: the loop is latency-bound
-                    uint32_t e[8];
+    const uint32_t total = per_frame * (uint32_t)d.nf;
+    for (uint32_t k0 = 0; warp + k0 * nwarp < total; k0 += 32u) {
+        const uint32_t pair = warp + (k0 + lane) * nwarp;
+        const uint32_t pf = pair < total ? pair / per_frame : 0u, pc = pair - pf * per_frame;
+        uint32_t* word = d.cnt + (size_t)pf * d.cnt_frame_stride + pc;
+        const uint32_t mine = (pair < total) ? min(__ldcg(word), ROUTE_REGION) : 0u; // written by a peer: read at L2
+        if (mine) *word = 0u;
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, mine != 0u);
+        while (todo) {
+            const int r = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t n = __shfl_sync(0xFFFFFFFFu, mine, r);
+            const uint32_t f = __shfl_sync(0xFFFFFFFFu, pf, r), c = __shfl_sync(0xFFFFFFFFu, pc, r);
+            const uint32_t* seg = d.inbox + (size_t)f * d.inbox_frame_stride + (size_t)c * ROUTE_REGION;
+            uint32_t* band = d.band[f];
+            for (uint32_t i0 = 0; i0 < n; i0 += 256u) { // 8 loads in flight per lane: the loop is latency-bound
+                uint32_t e[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t i = i0 + (uint32_t)j * 32u + lane;
-                        e[j] = i < n ? __ldcg(seg + i) : 0xFFFFFFFFu;
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t i = i0 + (uint32_t)j * 32u + lane;
+                    e[j] = i < n ? __ldcg(seg + i) : 0xFFFFFFFFu;
+                }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (e[j] >= d.band_cells) continue;
-                        band_add(band, e[j], CELLS == CELL_F16, d.wrap_w, d.halo, d.pitch);
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    if (e[j] >= d.band_cells) continue;
+                    band_add(band, e[j], CELLS == CELL_F16, d.wrap_w, d.halo, d.pitch);
                 }
             }
         }

@@ -22,6 +22,13 @@ __device__ __forceinline__ int32_t f2i32_x86(float f) {
     return (fabsf(f) < 2147483648.0f) ? __float2int_rz(f) : (int32_t)0x80000000;
 }
 
+// Both conversions of one coordinate from ONE F2I: i = __float2int_rz(f) is kept, and for f inside (-2^31, 2^31)
+// the uint32 the reference's fetch sees (cvttss2si r64, low half) is (uint32_t)i and the int32 its splat sees is i;
+// outside (or NaN), f2u32_x86 / f2i32_x86 give the answers.  The route kernel, which is issue-bound at per-rank
+// sizes, truncates a position once and uses it for the splat of this frame and the gather of the next.
+__device__ __forceinline__ uint32_t fetch_index(int32_t i, float f) { return fabsf(f) < 2147483648.0f ? (uint32_t)i : f2u32_x86(f); }
+__device__ __forceinline__ int32_t splat_index(int32_t i, float f) { return fabsf(f) < 2147483648.0f ? i : (int32_t)0x80000000; }
+
 // float -> uint8_t store of advect_points.cc:155 / splat_points.cc:155: cvttss2si r32, low byte.
 __device__ __forceinline__ uint32_t f2u8_x86(float f) {
     return (uint32_t)f2i32_x86(f) & 0xFFu;
