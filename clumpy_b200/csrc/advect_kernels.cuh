@@ -166,6 +166,7 @@ constexpr uint32_t ROUTE_BLOCK = ADVECT_THREADS * ADVECT_PTS; // points per CTA
 constexpr uint32_t ROUTE_REGION = ROUTE_BLOCK;                // entry slots per (CTA, destination, frame)
 constexpr int ROUTE_MAX_FUSE = ADVECT_MAX_FUSE;               // frames per launch
 constexpr int ROUTE_PARITIES = 4; // inbox slot sets in flight (see route_launch for why 4 is enough)
+constexpr uint32_t ROUTE_STAGE = 512; // entries per (frame, neighbour) a CTA collects in shared memory before they cross NVLink
 constexpr int ROUTE_SETS = 3;     // band-buffer sets: counted into | composited | being zeroed
 
 struct RouteDev {
@@ -200,29 +201,54 @@ __device__ __forceinline__ void band_add(uint32_t* __restrict__ band, uint32_t e
     }
 }
 
-// One entry for rank `dst`: the CTA-wide rank comes from a shared-memory atomic, the slot is fixed by
-// the CTA's region, the store goes over NVLink.
-__device__ __forceinline__ void route_send(const RouteDev& rt, int f, uint32_t* cta_n, int dst, uint32_t entry) {
+// Where entry r of this CTA for rank `dst` and frame f goes in dst's inbox.
+__device__ __forceinline__ uint32_t* route_slot(const RouteDev& rt, int f, int dst, uint32_t r) {
+    return rt.inbox[dst] + rt.inbox_off + (size_t)f * rt.inbox_frame_stride + ((size_t)rt.me * rt.nregion + blockIdx.x) * ROUTE_REGION + r;
+}
+
+// One entry for rank `dst`: the CTA-wide rank comes from a shared-memory atomic, the slot is fixed by the CTA's
+// region.  Entries for the two NEIGHBOURING ranks (nearly all of them with home-row shards) are collected in shared
+// memory -- stage[2][ROUTE_STAGE] of this frame -- and cross NVLink at the end of the launch as whole lines
+// (route_flush); a 4-byte store per entry, each its own 32-byte sector on the wire, cost a third of the kernel's
+// time at 8 GPUs.  What does not fit, or goes further away, is stored directly.
+__device__ __forceinline__ void route_send(const RouteDev& rt, int f, uint32_t* cta_n, uint32_t* stage, int dst, uint32_t entry) {
     const uint32_t r = atomicAdd(cta_n + dst, 1u);
-    rt.inbox[dst][rt.inbox_off + (size_t)f * rt.inbox_frame_stride + ((size_t)rt.me * rt.nregion + blockIdx.x) * ROUTE_REGION + r] = entry;
+    const int side = dst - rt.me; // -1 / +1: a neighbour
+    if ((side == -1 || side == 1) && r < ROUTE_STAGE) stage[(side > 0 ? ROUTE_STAGE : 0u) + r] = entry;
+    else *route_slot(rt, f, dst, r) = entry;
+}
+
+// The staged entries of every frame of the group, written to the neighbours' inboxes with coalesced stores: one
+// warp per (frame, side), lanes on consecutive slots.  Called by the whole CTA after a barrier.
+__device__ __forceinline__ void route_flush(const RouteDev& rt, const uint32_t (*cta_n)[ROUTE_MAX_WORLD],
+                                            const uint32_t (*stage)[2 * ROUTE_STAGE]) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (uint32_t b = warp; b < (uint32_t)rt.nf * 2u; b += nwarp) {
+        const int f = (int)(b >> 1), side = (int)(b & 1u), dst = rt.me + (side ? 1 : -1);
+        if (dst < 0 || dst >= rt.world) continue;
+        const uint32_t n = min(cta_n[f][dst], ROUTE_STAGE);
+        const uint32_t* src = stage[f] + (side ? ROUTE_STAGE : 0u);
+        uint32_t* out = route_slot(rt, f, dst, 0u);
+        for (uint32_t i = lane; i < n; i += 32u) out[i] = src[i];
+    }
 }
 
 // A cell of padded row `r` (relative to band `owner`'s first row) and padded column `ux`: counted
 // straight into this rank's band buffer when it is ours, sent to the owner's inbox otherwise; rows
 // within the sprite's reach of a band edge also go to the neighbouring band, whose composite needs them.
-__device__ __forceinline__ void route_cell(const RouteDev& rt, int f, uint32_t* cta_n, int owner, int r, uint32_t ux, int wrap_w) {
+__device__ __forceinline__ void route_cell(const RouteDev& rt, int f, uint32_t* cta_n, uint32_t* stage, int owner, int r, uint32_t ux, int wrap_w) {
     const uint32_t entry = (uint32_t)((r + rt.halo) * rt.pitch) + ux; // band rows: [halo above | chunk | halo below]
     if (owner == rt.me) band_add(rt.band[f], entry, rt.band_f16, wrap_w, rt.halo, rt.pitch);
-    else route_send(rt, f, cta_n, owner, entry);
+    else route_send(rt, f, cta_n, stage, owner, entry);
     if (r < rt.halo && owner > 0) {
         const uint32_t e = (uint32_t)((r + rt.chunk + rt.halo) * rt.pitch) + ux;
         if (owner - 1 == rt.me) band_add(rt.band[f], e, rt.band_f16, wrap_w, rt.halo, rt.pitch);
-        else route_send(rt, f, cta_n, owner - 1, e);
+        else route_send(rt, f, cta_n, stage, owner - 1, e);
     }
     if (r >= rt.chunk - rt.halo && owner < rt.world - 1) {
         const uint32_t e = (uint32_t)((r - rt.chunk + rt.halo) * rt.pitch) + ux;
         if (owner + 1 == rt.me) band_add(rt.band[f], e, rt.band_f16, wrap_w, rt.halo, rt.pitch);
-        else route_send(rt, f, cta_n, owner + 1, e);
+        else route_send(rt, f, cta_n, stage, owner + 1, e);
     }
 }
 
@@ -251,6 +277,7 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                     const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
                     uint32_t width, uint32_t height, float step, GeomDev g, RouteDev rt) {
     __shared__ uint32_t cta_n[ROUTE_MAX_FUSE][ROUTE_MAX_WORLD];
+    __shared__ uint32_t stage[SPLAT ? ROUTE_MAX_FUSE : 1][2 * ROUTE_STAGE]; // see route_send
     if (SPLAT) {
         if (threadIdx.x < ROUTE_MAX_FUSE * ROUTE_MAX_WORLD) (&cta_n[0][0])[threadIdx.x] = 0u;
         __syncthreads(); // here, where every warp arrives at once, not after the loads
@@ -330,14 +357,15 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                 owner = min((int)(uy / (uint32_t)rt.chunk), rt.world - 1);
                 r = (int)uy - owner * rt.chunk;
             }
-            route_cell(rt, f, cta_n[f], owner, r, ux, WRAP ? g.width : 0);
+            route_cell(rt, f, cta_n[f], stage[SPLAT ? f : 0], owner, r, ux, WRAP ? g.width : 0);
         }
     }
 #pragma unroll
     for (int k = 0; k < ADVECT_PTS; ++k)
         if (live[k]) st_stream_f2(pos + base + k * ADVECT_THREADS, p[k], pol);
     if (!SPLAT) return;
-    __syncthreads(); // every entry of this CTA is written, cta_n is final
+    __syncthreads(); // every entry of this CTA is written or staged, cta_n is final
+    route_flush(rt, cta_n, stage);
     // the non-zero counts go to their destinations (the receivers zero them again)
     uint32_t n = 0u;
     if (threadIdx.x < (uint32_t)(rt.nf * ROUTE_MAX_WORLD)) {
