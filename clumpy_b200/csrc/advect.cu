@@ -252,15 +252,15 @@ static int regroup_points(clumpy_advect* a) {
     const uint32_t n = a->npts;
     if (n == 0 || !a->sort_counts) return CLUMPY_OK;
     const SortGrid& sg = a->sort_grid;
-    const uint32_t pgrid = ceil_div(n, 256), nblocks = ceil_div(sg.ntiles, SCAN_BLOCK);
-    CK(cudaMemsetAsync(a->sort_counts, 0, (size_t)sg.ntiles * 4, ctx->stream));
+    const uint32_t pgrid = ceil_div(n, 256), nblocks = ceil_div(sg.nbins, SCAN_BLOCK);
+    CK(cudaMemsetAsync(a->sort_counts, 0, (size_t)sg.nbins * 4, ctx->stream));
     sort_count_kernel<<<pgrid, 256, 0, ctx->stream>>>(a->pos, n, sg, a->sort_counts);
     CK_LAUNCH(ctx);
-    scan_local_kernel<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(a->sort_counts, sg.ntiles, a->sort_sums);
+    scan_local_kernel<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(a->sort_counts, sg.nbins, a->sort_sums);
     CK_LAUNCH(ctx);
     scan_sums_kernel<<<1, SCAN_BLOCK, 0, ctx->stream>>>(a->sort_sums, nblocks);
     CK_LAUNCH(ctx);
-    scan_add_kernel<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(a->sort_counts, sg.ntiles, a->sort_sums);
+    scan_add_kernel<<<nblocks, SCAN_BLOCK, 0, ctx->stream>>>(a->sort_counts, sg.nbins, a->sort_sums);
     CK_LAUNCH(ctx);
     if (a->off16)
         regroup_scatter_kernel<uint16_t><<<pgrid, 256, 0, ctx->stream>>>(
@@ -306,10 +306,11 @@ static int sort_points(clumpy_advect* a, int regroup_opt) {
     }
     sg.tiles_x = ceil_div(a->width, 1u << sg.shift_x);
     sg.ntiles = (uint32_t)tiles(sg.shift_x, sg.shift_y);
+    sg.nbins = sg.ntiles + 2u * (a->width + 2u) + 2u * a->height; // + the ring of cells around the image (home_tile)
     a->sort_grid = sg;
     const size_t nalloc = std::max<size_t>((size_t)n + 1, 2);
-    DEV_ALLOC(ctx, &a->sort_counts, (size_t)sg.ntiles * 4);
-    DEV_ALLOC(ctx, &a->sort_sums, (size_t)ceil_div(sg.ntiles, SCAN_BLOCK) * 4);
+    DEV_ALLOC(ctx, &a->sort_counts, (size_t)sg.nbins * 4);
+    DEV_ALLOC(ctx, &a->sort_sums, (size_t)ceil_div(sg.nbins, SCAN_BLOCK) * 4);
     DEV_ALLOC(ctx, &a->pos_alt, nalloc * 8);
     DEV_ALLOC(ctx, &a->orig_alt, nalloc * 8);
     DEV_ALLOC(ctx, &a->offset_alt, nalloc * 4);
@@ -589,7 +590,7 @@ static void launch_advect_t(clumpy_advect* a, uint32_t phase, int nf, const Hist
             a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase,
             a->nframes, nf, g, ring);
     else
-        advect_fused_kernel<WRAP, MODE, OffT, 1><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
+        advect_fused_kernel<WRAP, MODE, OffT, 6><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>( // 6 CTAs per SM: 40 registers
             a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase,
             a->nframes, nf, g, ring);
 }

@@ -40,6 +40,18 @@ __device__ __forceinline__ void cell_add_f16(uint32_t* __restrict__ words, long 
 // (Warp-aggregated counts -- the lanes of a warp that hit the same cell sending ONE reduction, found with
 // match.any -- were measured in round 2 and lose: 0.0273 vs 0.0165 ms per frame for the route kernel at 2.1 M points,
 // profiles/r2_sweep_multi_2gpu_quarter.txt.  At 0.5 points per texel almost every lane has a cell of its own.)
+// Points OUTSIDE the image whose sprite still reaches it: a point that has left the image gets no velocity any more
+// (advect_points.cc:27-32) and sits still, just outside, until its reset -- at C4 some 60 of them per halo cell in
+// the steady state, every one reducing into the same cell every frame (one cell takes 0.65 G reductions per second).
+// The regroup stores such points in the order of their ring cell (home_tile), so the lanes of a warp share a few
+// cells: they find each other with match.any and send ONE reduction per cell.  Only lanes outside the image come
+// here; for the others (almost every lane its own cell) the match costs more than it saves (measured).
+__device__ __noinline__ void cell_add_f16_outside(uint32_t* __restrict__ words, long long cell) {
+    const uint32_t same = __match_any_sync(__activemask(), cell);
+    if ((uint32_t)(__ffs(same) - 1) != (threadIdx.x & 31u)) return;
+    const uint32_t h = (uint32_t)__half_as_ushort(__uint2half_rn((uint32_t)__popc(same))); // <= 32: exact
+    asm volatile("red.global.add.noftz.f16x2 [%0], %1;" :: "l"(words + (cell >> 1)), "r"((cell & 1) ? (h << 16) : h) : "memory");
+}
 __device__ __forceinline__ void cell_add_f16(uint32_t* __restrict__ words, long long cell, uint64_t pol) {
     const uint32_t one = (cell & 1) ? 0x3C000000u : 0x00003C00u;
     asm volatile("red.global.add.L2::cache_hint.noftz.f16x2 [%0], %1, %2;" :: "l"(words + (cell >> 1)), "r"(one), "l"(pol) : "memory");
@@ -60,6 +72,7 @@ __device__ __forceinline__ void count_point(uint32_t* __restrict__ hist, int32_t
     } else if (MODE == CELL_U32) {
         atomicAdd(hist + at, 1u);
     } else if (MODE == CELL_F16) {
+        if (!WRAP && ((uint32_t)cx >= (uint32_t)g.width || (uint32_t)cy >= (uint32_t)g.height)) { cell_add_f16_outside(hist, at); return; }
         cell_add_f16(hist, at, red_pol);
         if (WRAP && g.halo > 0) {
             int32_t m = cx % g.width;
@@ -166,7 +179,6 @@ constexpr uint32_t ROUTE_BLOCK = ADVECT_THREADS * ADVECT_PTS; // points per CTA
 constexpr uint32_t ROUTE_REGION = ROUTE_BLOCK;                // entry slots per (CTA, destination, frame)
 constexpr int ROUTE_MAX_FUSE = ADVECT_MAX_FUSE;               // frames per launch
 constexpr int ROUTE_PARITIES = 4; // inbox slot sets in flight (see route_launch for why 4 is enough)
-constexpr uint32_t ROUTE_STAGE = 512; // entries per (frame, neighbour) a CTA collects in shared memory before they cross NVLink
 constexpr int ROUTE_SETS = 3;     // band-buffer sets: counted into | composited | being zeroed
 
 struct RouteDev {
@@ -191,8 +203,9 @@ struct RouteDev {
 // One count into a band buffer.  Half cells in x-wrap mode (wrap_w = image width, else 0): the group
 // composite reads its halo columns as they are, so a cell within `halo` columns of the left / right edge is
 // also counted into the halo column on the other side (see count_point).
-__device__ __forceinline__ void band_add(uint32_t* __restrict__ band, uint32_t entry, int f16, int wrap_w, int halo, int pitch) {
+__device__ __forceinline__ void band_add(uint32_t* __restrict__ band, uint32_t entry, int f16, int wrap_w, int halo, int pitch, bool outside = false) {
     if (!f16) { atomicAdd(band + entry, 1u); return; }
+    if (outside) { cell_add_f16_outside(band, (long long)entry); return; } // (never in x-wrap mode: see count_point)
     cell_add_f16(band, (long long)entry);
     if (wrap_w && halo > 0) {
         const int m = (int)(entry % (uint32_t)pitch) - halo;
@@ -201,54 +214,31 @@ __device__ __forceinline__ void band_add(uint32_t* __restrict__ band, uint32_t e
     }
 }
 
-// Where entry r of this CTA for rank `dst` and frame f goes in dst's inbox.
-__device__ __forceinline__ uint32_t* route_slot(const RouteDev& rt, int f, int dst, uint32_t r) {
-    return rt.inbox[dst] + rt.inbox_off + (size_t)f * rt.inbox_frame_stride + ((size_t)rt.me * rt.nregion + blockIdx.x) * ROUTE_REGION + r;
-}
-
-// One entry for rank `dst`: the CTA-wide rank comes from a shared-memory atomic, the slot is fixed by the CTA's
-// region.  Entries for the two NEIGHBOURING ranks (nearly all of them with home-row shards) are collected in shared
-// memory -- stage[2][ROUTE_STAGE] of this frame -- and cross NVLink at the end of the launch as whole lines
-// (route_flush); a 4-byte store per entry, each its own 32-byte sector on the wire, cost a third of the kernel's
-// time at 8 GPUs.  What does not fit, or goes further away, is stored directly.
-__device__ __forceinline__ void route_send(const RouteDev& rt, int f, uint32_t* cta_n, uint32_t* stage, int dst, uint32_t entry) {
+// One entry for rank `dst`: the CTA-wide rank comes from a shared-memory atomic, the slot is fixed by
+// the CTA's region, the store goes over NVLink.  (Collecting a CTA's entries in shared memory and writing them out
+// as whole lines at the end of the launch was measured in round 2 and is SLOWER: 0.0198 vs 0.0163 ms per frame at
+// 2.1 M points per rank; the 4-byte stores are not what the kernel waits for.)
+__device__ __forceinline__ void route_send(const RouteDev& rt, int f, uint32_t* cta_n, int dst, uint32_t entry) {
     const uint32_t r = atomicAdd(cta_n + dst, 1u);
-    const int side = dst - rt.me; // -1 / +1: a neighbour
-    if ((side == -1 || side == 1) && r < ROUTE_STAGE) stage[(side > 0 ? ROUTE_STAGE : 0u) + r] = entry;
-    else *route_slot(rt, f, dst, r) = entry;
-}
-
-// The staged entries of every frame of the group, written to the neighbours' inboxes with coalesced stores: one
-// warp per (frame, side), lanes on consecutive slots.  Called by the whole CTA after a barrier.
-__device__ __forceinline__ void route_flush(const RouteDev& rt, const uint32_t (*cta_n)[ROUTE_MAX_WORLD],
-                                            const uint32_t (*stage)[2 * ROUTE_STAGE]) {
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (uint32_t b = warp; b < (uint32_t)rt.nf * 2u; b += nwarp) {
-        const int f = (int)(b >> 1), side = (int)(b & 1u), dst = rt.me + (side ? 1 : -1);
-        if (dst < 0 || dst >= rt.world) continue;
-        const uint32_t n = min(cta_n[f][dst], ROUTE_STAGE);
-        const uint32_t* src = stage[f] + (side ? ROUTE_STAGE : 0u);
-        uint32_t* out = route_slot(rt, f, dst, 0u);
-        for (uint32_t i = lane; i < n; i += 32u) out[i] = src[i];
-    }
+    rt.inbox[dst][rt.inbox_off + (size_t)f * rt.inbox_frame_stride + ((size_t)rt.me * rt.nregion + blockIdx.x) * ROUTE_REGION + r] = entry;
 }
 
 // A cell of padded row `r` (relative to band `owner`'s first row) and padded column `ux`: counted
 // straight into this rank's band buffer when it is ours, sent to the owner's inbox otherwise; rows
 // within the sprite's reach of a band edge also go to the neighbouring band, whose composite needs them.
-__device__ __forceinline__ void route_cell(const RouteDev& rt, int f, uint32_t* cta_n, uint32_t* stage, int owner, int r, uint32_t ux, int wrap_w) {
+__device__ __forceinline__ void route_cell(const RouteDev& rt, int f, uint32_t* cta_n, int owner, int r, uint32_t ux, int wrap_w, bool outside) {
     const uint32_t entry = (uint32_t)((r + rt.halo) * rt.pitch) + ux; // band rows: [halo above | chunk | halo below]
-    if (owner == rt.me) band_add(rt.band[f], entry, rt.band_f16, wrap_w, rt.halo, rt.pitch);
-    else route_send(rt, f, cta_n, stage, owner, entry);
+    if (owner == rt.me) band_add(rt.band[f], entry, rt.band_f16, wrap_w, rt.halo, rt.pitch, outside);
+    else route_send(rt, f, cta_n, owner, entry);
     if (r < rt.halo && owner > 0) {
         const uint32_t e = (uint32_t)((r + rt.chunk + rt.halo) * rt.pitch) + ux;
         if (owner - 1 == rt.me) band_add(rt.band[f], e, rt.band_f16, wrap_w, rt.halo, rt.pitch);
-        else route_send(rt, f, cta_n, stage, owner - 1, e);
+        else route_send(rt, f, cta_n, owner - 1, e);
     }
     if (r >= rt.chunk - rt.halo && owner < rt.world - 1) {
         const uint32_t e = (uint32_t)((r - rt.chunk + rt.halo) * rt.pitch) + ux;
         if (owner + 1 == rt.me) band_add(rt.band[f], e, rt.band_f16, wrap_w, rt.halo, rt.pitch);
-        else route_send(rt, f, cta_n, stage, owner + 1, e);
+        else route_send(rt, f, cta_n, owner + 1, e);
     }
 }
 
@@ -277,7 +267,6 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                     const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
                     uint32_t width, uint32_t height, float step, GeomDev g, RouteDev rt) {
     __shared__ uint32_t cta_n[ROUTE_MAX_FUSE][ROUTE_MAX_WORLD];
-    __shared__ uint32_t stage[SPLAT ? ROUTE_MAX_FUSE : 1][2 * ROUTE_STAGE]; // see route_send
     if (SPLAT) {
         if (threadIdx.x < ROUTE_MAX_FUSE * ROUTE_MAX_WORLD) (&cta_n[0][0])[threadIdx.x] = 0u;
         __syncthreads(); // here, where every warp arrives at once, not after the loads
@@ -346,7 +335,7 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                 if (ux >= padded_w) continue;
             }
             int r = (int)uy - my_lo;
-            if (!WRAP && (uint32_t)(r - rt.halo) < interior) { // own band, away from its edges
+            if (!WRAP && (uint32_t)(r - rt.halo) < interior && (uint32_t)cx < (uint32_t)g.width) { // own band, away from its edges, inside the image
                 const uint32_t entry = (uint32_t)((r + rt.halo) * rt.pitch) + ux;
                 if (F16) cell_add_f16(band, (long long)entry);
                 else atomicAdd(band + entry, 1u);
@@ -357,15 +346,15 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                 owner = min((int)(uy / (uint32_t)rt.chunk), rt.world - 1);
                 r = (int)uy - owner * rt.chunk;
             }
-            route_cell(rt, f, cta_n[f], stage[SPLAT ? f : 0], owner, r, ux, WRAP ? g.width : 0);
+            const bool outside = !WRAP && ((uint32_t)cx >= (uint32_t)g.width || (uint32_t)cy >= (uint32_t)g.height);
+            route_cell(rt, f, cta_n[f], owner, r, ux, WRAP ? g.width : 0, outside);
         }
     }
 #pragma unroll
     for (int k = 0; k < ADVECT_PTS; ++k)
         if (live[k]) st_stream_f2(pos + base + k * ADVECT_THREADS, p[k], pol);
     if (!SPLAT) return;
-    __syncthreads(); // every entry of this CTA is written or staged, cta_n is final
-    route_flush(rt, cta_n, stage);
+    __syncthreads(); // every entry of this CTA is written, cta_n is final
     // the non-zero counts go to their destinations (the receivers zero them again)
     uint32_t n = 0u;
     if (threadIdx.x < (uint32_t)(rt.nf * ROUTE_MAX_WORLD)) {
@@ -480,15 +469,26 @@ drain_group_kernel(DrainDev d) {
 
 struct SortGrid {
     int shift_x, shift_y; // tile = 2^shift_x x 2^shift_y texels
-    uint32_t tiles_x, ntiles;
+    uint32_t tiles_x, ntiles; // ntiles: the tiles of the image, then the cells of the ring around it
     uint32_t width, height;
+    uint32_t nbins;           // tiles + ring cells
 };
 
+// The sort key of a point: the tile it is in -- or, for a point OUTSIDE the image, the cell of the one-texel ring
+// around the image nearest to it (top row, bottom row, left column, right column), so that the points that sit
+// still out there end up ordered by the cell they reduce into (cell_add_f16_outside).
 __device__ __forceinline__ uint32_t home_tile(float2 p, const SortGrid& sg) {
-    int32_t x = f2i32_x86(p.x), y = f2i32_x86(p.y);
-    x = max(0, min(x, (int32_t)sg.width - 1));
-    y = max(0, min(y, (int32_t)sg.height - 1));
-    return (uint32_t)(y >> sg.shift_y) * sg.tiles_x + (uint32_t)(x >> sg.shift_x);
+    const int32_t x = f2i32_x86(p.x), y = f2i32_x86(p.y);
+    const int32_t w = (int32_t)sg.width, h = (int32_t)sg.height;
+    if ((uint32_t)x < sg.width && (uint32_t)y < sg.height)
+        return (uint32_t)(y >> sg.shift_y) * sg.tiles_x + (uint32_t)(x >> sg.shift_x);
+    const int32_t cx = max(-1, min(x, w)), cy = max(-1, min(y, h));
+    uint32_t ring;
+    if (cy < 0) ring = (uint32_t)(cx + 1);                              // above: columns -1 .. w
+    else if (cy >= h) ring = (uint32_t)(w + 2) + (uint32_t)(cx + 1);    // below
+    else if (cx < 0) ring = 2u * (uint32_t)(w + 2) + (uint32_t)cy;      // left: rows 0 .. h-1
+    else ring = 2u * (uint32_t)(w + 2) + (uint32_t)h + (uint32_t)cy;    // right
+    return sg.ntiles + ring;
 }
 
 __global__ void __launch_bounds__(256)

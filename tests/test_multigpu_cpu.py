@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from clumpy_b200.multigpu import BandPlan, exchange_counts, field_rows, shard_indices, shard_range
+from clumpy_b200.multigpu import BandPlan, exchange_counts, field_rows, shard_indices, shard_range, strip_edges
 
 
 def test_shard_range_covers_everything():
@@ -114,3 +114,32 @@ def test_exchange_counts_over_gloo(world, height, halo):
         out = m.dict()
         mp.spawn(_worker, args=(world, port, height, halo, 40, out), nprocs=world, join=True)
         assert all(out[r] for r in range(world)), dict(out)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_strip_edges_agree_with_shard_indices(world):
+    """The row strips a rank derives from the row histogram (what the device-side shard selection uses, and what the
+    C++ driver restates in csrc/advect_multi.cu) are the strips shard_indices cuts on the host."""
+    rng = np.random.default_rng(11)
+    h = 137
+    for pts in ((rng.random((20000, 2)) * [90, h]).astype(np.float32),
+                rng.normal([40, 30], [10, 9], (20000, 2)).astype(np.float32),
+                np.full((500, 2), 5.5, np.float32), np.zeros((0, 2), np.float32)):
+        row = np.clip(np.nan_to_num(pts[:, 1].astype(np.float64)), 0, h - 1).astype(np.int64)
+        rows = np.bincount(row, minlength=h)
+        edges = strip_edges(rows, world)
+        assert edges[0] == 0 and edges[-1] == h and all(a <= b for a, b in zip(edges, edges[1:]))
+        for r in range(world):
+            want = shard_indices(pts, h, world, r)
+            got = np.nonzero((row >= edges[r]) & (row < edges[r + 1]))[0]
+            assert np.array_equal(want, got)
+
+
+def test_band_plan_ranks_without_rows():
+    """More padded rows than the image has (8 ranks on 200 rows): the last rank's chunk lies in the padding and it
+    owns no rows -- and says so with an empty range inside the image."""
+    plan = BandPlan(200, 1, 256, 8)
+    spans = [plan.owned_rows(r) for r in range(8)]
+    assert spans[-1][0] == spans[-1][1] <= 200
+    covered = sorted(y for a, b in spans for y in range(a, b))
+    assert covered == list(range(200))
