@@ -36,7 +36,8 @@ using namespace clumpy;
 
 namespace {
 
-constexpr int NSETS = ROUTE_SETS;                       // counter-image sets of the group path
+constexpr int NSETS = 3;                                // counter-image sets of the single-GPU group path: counted into | composited | being zeroed
+constexpr int RSETS = ROUTE_SETS;                       // band-buffer sets of the routed path
 constexpr int MAX_HIST = NSETS * ADVECT_MAX_FUSE;       // counter images at most
 constexpr int MAX_IMAGES = 2 * ADVECT_MAX_FUSE + 2;     // framebuffers at most (recorded frames in flight)
 constexpr int LEGACY_RING = 8;                          // counter images of the u32 / exact-order path
@@ -133,13 +134,13 @@ struct clumpy_advect {
         uint32_t* inbox = nullptr;   // [ROUTE_PARITIES][ROUTE_MAX_FUSE][world][nregion * ROUTE_REGION] cell indices, then
                                      // [ROUTE_PARITIES][ROUTE_MAX_FUSE][world][nregion] count words, then [world] epoch flags
         size_t entries_per_frame = 0, cnt_per_frame = 0, cnt_offset = 0, flags_offset = 0; // in uint32 units
-        uint32_t* band = nullptr;    // NSETS x ROUTE_MAX_FUSE band buffers of [halo | chunk | halo | slack] rows
+        uint32_t* band = nullptr;    // RSETS x ROUTE_MAX_FUSE band buffers of [halo | chunk | halo | slack] rows
         size_t band_bytes = 0;       // bytes of ONE band buffer (a multiple of 256)
         uint32_t band_cells = 0;
-        uint64_t group_index = 0;    // groups that splatted so far: parity = % ROUTE_PARITIES, set = % NSETS
-        int set_used[NSETS] = {0, 0, 0};
-        cudaEvent_t routed = nullptr, composited[NSETS] = {};
-        bool composited_pending[NSETS] = {false, false, false};
+        uint64_t group_index = 0;    // groups that splatted so far: parity = % ROUTE_PARITIES, set = % RSETS
+        int set_used[RSETS] = {};
+        cudaEvent_t routed = nullptr, composited[RSETS] = {};
+        bool composited_pending[RSETS] = {};
         uint32_t* ticket = nullptr;
         uint32_t* peer_inbox[ROUTE_MAX_WORLD] = {nullptr};
         uint32_t* errors = nullptr;      // pinned, mapped: fence time-outs seen by this rank's drain kernels
@@ -147,6 +148,7 @@ struct clumpy_advect {
         unsigned long long timeout_ns = 2000000000ull;
         uint32_t epoch = 0;          // epoch of the last group launched
         bool loopback = false;       // CLUMPY_ROUTE_LOOPBACK=1: see route_begin
+        bool pipeline = true;        // the drain of a group rides on a later route launch (CLUMPY_ROUTE_PIPELINE=0: never)
     } route;
 };
 
@@ -217,10 +219,8 @@ static void advect_release(clumpy_advect* a) {
     }
     if (a->route.inbox_owned) cudaFree(a->route.inbox); // peers map it: a plain allocation
     if (a->route.errors) cudaFreeHost(a->route.errors);
-    for (int s = 0; s < NSETS; ++s) {
-        if (a->set_composited[s]) cudaEventDestroy(a->set_composited[s]);
-        if (a->route.composited[s]) cudaEventDestroy(a->route.composited[s]);
-    }
+    for (int s = 0; s < NSETS; ++s) if (a->set_composited[s]) cudaEventDestroy(a->set_composited[s]);
+    for (int s = 0; s < RSETS; ++s) if (a->route.composited[s]) cudaEventDestroy(a->route.composited[s]);
     if (a->route.routed) cudaEventDestroy(a->route.routed);
     free_group_table(&a->gtab);
     for (int b = 0; b < LEGACY_RING; ++b) if (a->cleared[b]) cudaEventDestroy(a->cleared[b]);
@@ -976,7 +976,7 @@ static uint32_t* route_band(const clumpy_advect* adv, int set, int f) {
 }
 
 template <bool WRAP, bool SPLAT, bool F16, typename OffT>
-static void launch_route_t(clumpy_advect* a, const RouteDev& rd) {
+static void launch_route_t(clumpy_advect* a, const RouteDev& rd, const DrainDev& carried) {
     const uint32_t grid = ceil_div(a->npts, ROUTE_BLOCK); // CTA c owns region c of its segments
     const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch, a->keep_pos ? 1 : 0, 0};
     // CLUMPY_ROUTE_SMEM_KB=<n> (A/B): n KB of unused dynamic shared memory per CTA, to cap how many CTAs of this
@@ -984,10 +984,10 @@ static void launch_route_t(clumpy_advect* a, const RouteDev& rd) {
     const size_t pad = (size_t)std::min(std::max(env_int("CLUMPY_ROUTE_SMEM_KB", 0), 0), 48) * 1024;
     if (a->route.minb == 8)
         advect_route_kernel<WRAP, SPLAT, F16, OffT, 8><<<grid, ADVECT_THREADS, pad, a->ctx->stream>>>(
-            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);
+            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd, carried);
     else
         advect_route_kernel<WRAP, SPLAT, F16, OffT, 6><<<grid, ADVECT_THREADS, pad, a->ctx->stream>>>(
-            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);
+            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd, carried);
 }
 
 static size_t route_inbox_layout(uint32_t capacity, int world, uint32_t* nregion, size_t* entries_per_frame, size_t* cnt_per_frame,
@@ -1049,8 +1049,8 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
         CK(cudaMalloc(&rt.inbox, ibytes)); // mapped by the peers: a plain allocation, not the pool
     }
     trace_mark(ctx, "route_begin: inbox allocation");
-    DEV_ALLOC(ctx, &rt.band, (size_t)NSETS * ROUTE_MAX_FUSE * rt.band_bytes);
-    for (int s = 0; s < NSETS; ++s) CK(cudaEventCreateWithFlags(&rt.composited[s], cudaEventDisableTiming));
+    DEV_ALLOC(ctx, &rt.band, (size_t)RSETS * ROUTE_MAX_FUSE * rt.band_bytes);
+    for (int s = 0; s < RSETS; ++s) CK(cudaEventCreateWithFlags(&rt.composited[s], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&rt.routed, cudaEventDisableTiming));
     CK(cudaHostAlloc(&rt.errors, sizeof(uint32_t), cudaHostAllocMapped));
     *rt.errors = 0u;
@@ -1059,7 +1059,7 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     CK(cudaMemsetAsync(rt.ticket, 0, sizeof(uint32_t), ctx->stream));
     // count words and flags start at zero (the entries need no initialisation)
     CK(cudaMemsetAsync(rt.inbox + rt.cnt_offset, 0, ibytes - rt.cnt_offset * sizeof(uint32_t), ctx->stream));
-    CK(cudaMemsetAsync(rt.band, 0, (size_t)NSETS * ROUTE_MAX_FUSE * rt.band_bytes, ctx->stream));
+    CK(cudaMemsetAsync(rt.band, 0, (size_t)RSETS * ROUTE_MAX_FUSE * rt.band_bytes, ctx->stream));
     // Load every kernel of the frame loop NOW.  With lazy module loading the first launch of a kernel
     // can block the host until the device is idle -- and a drain kernel may be sitting on the device
     // waiting for the epoch of a rank that this very host thread has yet to launch (one process
@@ -1102,6 +1102,7 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     // publishes all `world` epochs into its own flags.  Timing and memory traffic are about those of a
     // real rank, the FRAMES ARE NOT (entries for other bands pile up in this rank's inbox).
     rt.loopback = env_int("CLUMPY_ROUTE_LOOPBACK", 0) == 1;
+    rt.pipeline = env_int("CLUMPY_ROUTE_PIPELINE", 1) != 0;
     rt.on = true;
     *inbox_dev = rt.inbox;
     if (rt.inbox_owned) *inbox_bytes = ibytes;
@@ -1116,34 +1117,62 @@ CLUMPY_API int clumpy_cuda_advect_route_peers(clumpy_advect* adv, void* const* p
     return CLUMPY_OK;
 }
 
-struct RouteEvents { cudaEvent_t r0, r1, d0, d1, c1; };
+struct RouteEvents { cudaEvent_t r0, r1, d0, d1, c1; bool keep_overlap = false; };
 
-// One group of `nf` frames of the routed run, all three stages enqueued:
+// One group of `nf` frames of the routed run has a SENDING half and a RECEIVING half:
 //
-//   main stream    advect_route_kernel: Euler step + reset of this rank's points through the group; own-band
-//                  points are counted into band buffer (set, f), the others' cells are stored into their
-//                  owners' inboxes (parity); at its end the group's epoch goes to every peer
-//   side stream    drain_group_kernel (waits for every peer's epoch, counts the inbox into the band buffers),
-//                  then the group composite of this rank's image rows, which also zeroes the band buffers
-//                  of the group before
+//   route_front   main stream: advect_route_kernel -- Euler step + reset of this rank's points through the group;
+//                 own-band points are counted into band buffer (set, f), the others' cells are stored into their
+//                 owners' inboxes (parity); at its end the group's epoch goes to every peer
+//   route_back    the entries the peers sent are counted into the band buffers (the "drain"), then the group
+//                 composite of this rank's image rows runs on the side stream; it also zeroes the band buffers of
+//                 the group before
 //
-// What may be reused when (G = this group; "its" = this rank's):
-//   band set G % 3 was read by composite(G - 3) and zeroed by composite(G - 2): the route launch waits for
-//     its composite(G - 2);
-//   inbox parity G % 4 was last written for group G - 4 and read by the PEERS' drain(G - 4).  Its composite(G - 2)
-//     is behind its drain(G - 2), which saw every peer's epoch G - 2, i.e. every peer's route(G - 2) had
-//     run, which that peer launched behind ITS composite(G - 4) and therefore behind its drain(G - 4).  So the
-//     same wait covers the inbox: four parities are enough and no peer is ever waited for on the host.
-static int route_group(clumpy_advect* adv, uint32_t nf, RecordSink* sink, RouteEvents* ev) {
+// Inside one call the two halves are PIPELINED (route_steps_impl): the drain of group G rides on the route launch
+// of group G + 2 (`carried`), behind a one-CTA launch that waits for the peers' epochs G -- which by then have been
+// out for a whole group, so the ranks only pace each other loosely -- and composite(G) follows that launch on the
+// side stream, beside route(G + 3).  The groups still in flight at the end of a call (and every group of a profiled
+// or non-overlapping run) take the stand-alone form: drain_group_kernel (wait + count) and the composite.
+// Before round 2's last change every drain was such a launch on the side stream; the timeline (CLUMPY_ROUTE_TIMELINE)
+// showed it starved of SM slots by the route grid beside it (105 us instead of 40) and the route launches gated by
+// the side stream.
+//
+// What may be reused when (G = this group; "its" = this rank's; ROUTE_SETS = 5, ROUTE_PARITIES = 8):
+//   band set G % 5 was read by composite(G - 5) and zeroed by composite(G - 4): route(G) waits for its
+//     composite(G - 4), which was enqueued behind route(G - 2) at the latest -- so the wait never holds route(G)
+//     back behind route(G - 1), the launch in front of it, as it did with three and four sets;
+//   inbox parity G % 8 was last written for group G - 8 and read by the PEERS' drain(G - 8), carried or not.  Its
+//     composite(G - 4) is behind its drain(G - 4), which ran behind a wait for every peer's epoch G - 4: every
+//     peer's route(G - 4) had started, which that peer launched behind ITS composite(G - 8) and therefore behind
+//     its drain(G - 8).  So the same wait covers the inbox, in any mix of pipelined and stand-alone groups: eight
+//     parities are enough and no peer is ever waited for on the host.
+struct RouteBack { uint32_t nf = 0; int set = 0, parity = 0; uint32_t epoch = 0; };
+
+static DrainDev route_drain_desc(const clumpy_advect* adv, const RouteBack& b, bool wait) {
+    const auto& rt = adv->route;
+    DrainDev dd = {};
+    dd.inbox = rt.inbox + (size_t)b.parity * ROUTE_MAX_FUSE * rt.entries_per_frame;
+    dd.cnt = rt.inbox + rt.cnt_offset + (size_t)b.parity * ROUTE_MAX_FUSE * rt.cnt_per_frame;
+    dd.inbox_frame_stride = rt.entries_per_frame; dd.cnt_frame_stride = rt.cnt_per_frame;
+    dd.nregion = rt.nregion; dd.world = rt.world; dd.nf = (int)b.nf;
+    dd.flags = wait ? rt.inbox + rt.flags_offset : nullptr;
+    dd.epoch = b.epoch; dd.errors = rt.errors_dev; dd.timeout_ns = rt.timeout_ns;
+    for (uint32_t f = 0; f < b.nf; ++f) dd.band[f] = route_band(adv, b.set, (int)f);
+    dd.band_cells = rt.band_cells;
+    dd.wrap_w = adv->wrapx ? (int)adv->width : 0; dd.halo = adv->geom.halo; dd.pitch = adv->geom.pitch;
+    return dd;
+}
+
+// The sending half.  `carried`: an earlier group whose entries this launch counts on its way out (or NULL).
+// *back describes this group's receiving half (nf == 0: the group does not splat, nothing to receive).
+static int route_front(clumpy_advect* adv, uint32_t nf, const RouteBack* carried, RouteEvents* ev, RouteBack* back) {
     clumpy_cuda_ctx* ctx = adv->ctx;
     auto& rt = adv->route;
     const bool splat = frame_splats(adv);
-    const bool overlap = adv->overlap && !ev;
     const cudaStream_t main_stream = ctx->stream;
-    const cudaStream_t side = overlap ? ctx->aux_stream : main_stream;
-    const int set = (int)(rt.group_index % NSETS), parity = (int)(rt.group_index % ROUTE_PARITIES);
+    const int set = (int)(rt.group_index % RSETS), parity = (int)(rt.group_index % ROUTE_PARITIES);
     if (splat) {
-        const int z = (set + 1) % NSETS; // the set of group G - 2
+        const int z = (set + 1) % RSETS; // the set of group G - 4, whose composite zeroed the set of group G - 5: this one
         if (rt.composited_pending[z]) {
             CK(cudaStreamWaitEvent(main_stream, rt.composited[z], 0));
             rt.composited_pending[z] = false;
@@ -1168,109 +1197,119 @@ static int route_group(clumpy_advect* adv, uint32_t nf, RecordSink* sink, RouteE
         rd.cnt[r] = rt.peer_inbox[r] + rt.cnt_offset;
         rd.flags[r] = rt.peer_inbox[r] + rt.flags_offset;
     }
+    DrainDev carry = {};
+    if (carried) {
+        // the wait alone, one CTA: the peers' epochs of the carried group (bounded; a time-out is recorded and the
+        // counting goes ahead on whatever arrived -- the host fails the call on the error count)
+        RouteBack none = *carried;
+        none.nf = 0;
+        const DrainDev wd = route_drain_desc(adv, none, true);
+        if (adv->cell_mode == CELL_F16) drain_group_kernel<CELL_F16><<<1, 32, 0, main_stream>>>(wd);
+        else drain_group_kernel<CELL_U32><<<1, 32, 0, main_stream>>>(wd);
+        CK_LAUNCH(ctx);
+        carry = route_drain_desc(adv, *carried, false);
+    }
     if (ev) CK(cudaEventRecord(ev->r0, main_stream));
     if (adv->npts) {
-#define ROUTE_LAUNCH(W, S) (adv->cell_mode == CELL_F16 ? (adv->off16 ? launch_route_t<W, S, true, uint16_t>(adv, rd) : launch_route_t<W, S, true, uint32_t>(adv, rd)) \
-                                                       : (adv->off16 ? launch_route_t<W, S, false, uint16_t>(adv, rd) : launch_route_t<W, S, false, uint32_t>(adv, rd)))
+#define ROUTE_LAUNCH(W, S) (adv->cell_mode == CELL_F16 ? (adv->off16 ? launch_route_t<W, S, true, uint16_t>(adv, rd, carry) : launch_route_t<W, S, true, uint32_t>(adv, rd, carry)) \
+                                                       : (adv->off16 ? launch_route_t<W, S, false, uint16_t>(adv, rd, carry) : launch_route_t<W, S, false, uint32_t>(adv, rd, carry)))
         if (adv->wrapx) { if (splat) ROUTE_LAUNCH(true, true); else ROUTE_LAUNCH(true, false); }
         else            { if (splat) ROUTE_LAUNCH(false, true); else ROUTE_LAUNCH(false, false); }
 #undef ROUTE_LAUNCH
         CK_LAUNCH(ctx);
-    } else if (splat) { // no route kernel to carry the fence
+    } else if (splat) { // no route kernel to carry the fence (and nothing is ever carried: see route_steps_impl)
         route_signal_kernel<<<1, 32, 0, main_stream>>>(rd);
         CK_LAUNCH(ctx);
     }
     if (ev) CK(cudaEventRecord(ev->r1, main_stream));
-    int slot[ADVECT_MAX_FUSE];
-    cudaEvent_t ready = adv->frames_ready;
+    *back = RouteBack();
     if (splat) {
         rt.epoch += 1u;
-        if (overlap) {
-            // the receiving half starts once this rank's own route kernel is done (by then its own epoch is
-            // out; a drain that started earlier would only sit on SM slots waiting for it)
-            CK(cudaEventRecord(rt.routed, main_stream));
-            CK(cudaStreamWaitEvent(side, rt.routed, 0));
-        }
-        if (ev) CK(cudaEventRecord(ev->d0, side));
-        DrainDev dd = {};
-        dd.inbox = rt.inbox + rd.inbox_off; dd.cnt = rt.inbox + rt.cnt_offset + rd.cnt_off;
-        dd.inbox_frame_stride = rt.entries_per_frame; dd.cnt_frame_stride = rt.cnt_per_frame;
-        dd.nregion = rt.nregion; dd.world = rt.world; dd.nf = (int)nf;
-        dd.flags = rt.inbox + rt.flags_offset; dd.epoch = rt.epoch; dd.errors = rt.errors_dev; dd.timeout_ns = rt.timeout_ns;
-        for (uint32_t f = 0; f < nf; ++f) dd.band[f] = rd.band[f];
-        dd.band_cells = rt.band_cells;
-        dd.wrap_w = adv->wrapx ? (int)adv->width : 0; dd.halo = adv->geom.halo; dd.pitch = adv->geom.pitch;
-        // A small grid: these CTAs may sit waiting for a peer's epoch while route kernels run on the
-        // main stream, and must leave them most of the SMs.
+        back->nf = nf; back->set = set; back->parity = parity; back->epoch = rt.epoch;
+        rt.group_index++;
+    }
+    adv->simframe += nf;
+    adv->frames_since_regroup += nf;
+    if (adv->regroup_every && adv->frames_since_regroup >= adv->regroup_every) return regroup_points(adv);
+    return CLUMPY_OK;
+}
+
+// The receiving half of group `b` (in group order).  `counted`: a route launch already carried the drain.
+static int route_back(clumpy_advect* adv, const RouteBack& b, bool counted, bool overlap, RecordSink* sink, RouteEvents* ev) {
+    clumpy_cuda_ctx* ctx = adv->ctx;
+    auto& rt = adv->route;
+    const cudaStream_t main_stream = ctx->stream;
+    const cudaStream_t side = overlap ? ctx->aux_stream : main_stream;
+    const uint32_t nf = b.nf;
+    const int set = b.set;
+    int slot[ADVECT_MAX_FUSE];
+    if (overlap) {
+        // behind the launches of the main stream so far: this rank's own counts of the group and (counted) the
+        // route launch that carried its drain; a stand-alone drain that started earlier would only sit on SM
+        // slots waiting for this rank's own epoch
+        CK(cudaEventRecord(rt.routed, main_stream));
+        CK(cudaStreamWaitEvent(side, rt.routed, 0));
+    }
+    if (ev) CK(cudaEventRecord(ev->d0, side));
+    if (!counted) {
+        const DrainDev dd = route_drain_desc(adv, b, true);
         // 16 (frame, region) pairs per warp; the CTAs wait (one thread each) for the peers' epochs before they work
         const uint32_t dgrid = std::min<uint32_t>((uint32_t)ctx->sm_count * 8u, std::max<uint32_t>(1u, ceil_div((uint32_t)(nf * rt.cnt_per_frame), 16u * 8u)));
         if (adv->cell_mode == CELL_F16) drain_group_kernel<CELL_F16><<<dgrid, 256, 0, side>>>(dd);
         else drain_group_kernel<CELL_U32><<<dgrid, 256, 0, side>>>(dd);
         CK_LAUNCH(ctx);
-        if (ev) CK(cudaEventRecord(ev->d1, side));
-        // image rows this rank owns: those whose window of padded rows lies in chunk + halos
-        const int h = adv->geom.halo, lo = rt.rank * rt.chunk;
-        const int y0 = std::max(0, lo - h), y1 = route_last_row(adv);
-        const size_t cell_bytes = cell_bytes_of(adv->cell_mode);
-        const size_t row_off = (size_t)(y0 - (lo - h)) * adv->geom.pitch * cell_bytes;
-        const int prev = (set + NSETS - 1) % NSETS;
-        int rc = choose_frame_images(adv, side, nf, sink != nullptr, slot);
-        if (rc) return rc;
-        if (adv->cell_mode == CELL_F16) {
-            GroupCompositeArgs ca;
-            ca.width = adv->geom.width; ca.height = std::max(0, y1 - y0); ca.pitch = adv->geom.pitch; ca.img_pitch = (int)adv->width;
-            ca.nf = (int)nf;
-            ca.img_in = adv->imgs[adv->cur] + (size_t)y0 * adv->width;
-            for (uint32_t f = 0; f < nf; ++f) {
-                ca.cells[f] = reinterpret_cast<const char*>(rd.band[f]) + row_off;
-                ca.frame_out[f] = slot[f] >= 0 ? adv->imgs[slot[f]] + (size_t)y0 * adv->width : nullptr;
-            }
-            ca.nzero = rt.set_used[prev];
-            for (int zf = 0; zf < ca.nzero; ++zf) {
-                ca.zero[zf] = reinterpret_cast<uint4*>(route_band(adv, prev, zf));
-                ca.zero_n16[zf] = (uint32_t)(rt.band_bytes / 16);
-            }
-            if (ca.height <= 0) { // a rank without image rows still has band buffers to zero
-                for (int zf = 0; zf < ca.nzero; ++zf) CK(cudaMemsetAsync(ca.zero[zf], 0, rt.band_bytes, side));
-            } else {
-                rc = launch_composite_group(ctx, side, adv->gtab, ca);
-                if (rc) return rc;
-            }
-        } else {
-            for (int zf = 0; zf < rt.set_used[prev]; ++zf) CK(cudaMemsetAsync(route_band(adv, prev, zf), 0, rt.band_bytes, side));
-            for (uint32_t f = 0; f < nf && y1 > y0; ++f) {
-                const int dst = slot[f] >= 0 ? slot[f] : adv->cur;
-                HistGeom g = adv->geom;
-                g.height = y1 - y0;
-                ctx->stream = side;
-                rc = launch_composite(ctx, g, adv->rings, reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(rd.band[f]) + row_off),
-                                      adv->wrapx, 1, adv->decay, adv->imgs[adv->cur] + (size_t)y0 * adv->width, adv->imgs[dst] + (size_t)y0 * adv->width);
-                ctx->stream = main_stream;
-                if (rc) return rc;
-                adv->cur = dst;
-            }
+    }
+    if (ev) CK(cudaEventRecord(ev->d1, side));
+    // image rows this rank owns: those whose window of padded rows lies in chunk + halos
+    const int h = adv->geom.halo, lo = rt.rank * rt.chunk;
+    const int y0 = std::max(0, lo - h), y1 = route_last_row(adv);
+    const size_t cell_bytes = cell_bytes_of(adv->cell_mode);
+    const size_t row_off = (size_t)(y0 - (lo - h)) * adv->geom.pitch * cell_bytes;
+    const int prev = (set + RSETS - 1) % RSETS;
+    int rc = choose_frame_images(adv, side, nf, sink != nullptr, slot);
+    if (rc) return rc;
+    if (adv->cell_mode == CELL_F16) {
+        GroupCompositeArgs ca;
+        ca.width = adv->geom.width; ca.height = std::max(0, y1 - y0); ca.pitch = adv->geom.pitch; ca.img_pitch = (int)adv->width;
+        ca.nf = (int)nf;
+        ca.img_in = adv->imgs[adv->cur] + (size_t)y0 * adv->width;
+        for (uint32_t f = 0; f < nf; ++f) {
+            ca.cells[f] = reinterpret_cast<const char*>(route_band(adv, set, (int)f)) + row_off;
+            ca.frame_out[f] = slot[f] >= 0 ? adv->imgs[slot[f]] + (size_t)y0 * adv->width : nullptr;
         }
-        rt.set_used[prev] = 0;
-        rt.set_used[set] = (int)nf;
-        adv->cur = slot[nf - 1];
-        CK(cudaEventRecord(rt.composited[set], side));
-        rt.composited_pending[set] = overlap;
-        ready = rt.composited[set];
-        if (ev) CK(cudaEventRecord(ev->c1, side));
-        if (overlap) adv->side_dirty = true;
-        rt.group_index++;
+        ca.nzero = rt.set_used[prev];
+        for (int zf = 0; zf < ca.nzero; ++zf) {
+            ca.zero[zf] = reinterpret_cast<uint4*>(route_band(adv, prev, zf));
+            ca.zero_n16[zf] = (uint32_t)(rt.band_bytes / 16);
+        }
+        if (ca.height <= 0) { // a rank without image rows still has band buffers to zero
+            for (int zf = 0; zf < ca.nzero; ++zf) CK(cudaMemsetAsync(ca.zero[zf], 0, rt.band_bytes, side));
+        } else {
+            rc = launch_composite_group(ctx, side, adv->gtab, ca);
+            if (rc) return rc;
+        }
     } else {
-        if (ev) { CK(cudaEventRecord(ev->d0, side)); CK(cudaEventRecord(ev->d1, side)); CK(cudaEventRecord(ev->c1, side)); }
-        for (uint32_t f = 0; f < nf; ++f) slot[f] = adv->cur;
-        if (sink) CK(cudaEventRecord(ready, side));
+        for (int zf = 0; zf < rt.set_used[prev]; ++zf) CK(cudaMemsetAsync(route_band(adv, prev, zf), 0, rt.band_bytes, side));
+        for (uint32_t f = 0; f < nf && y1 > y0; ++f) {
+            const int dst = slot[f] >= 0 ? slot[f] : adv->cur;
+            HistGeom g = adv->geom;
+            g.height = y1 - y0;
+            ctx->stream = side;
+            rc = launch_composite(ctx, g, adv->rings, reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(route_band(adv, set, (int)f)) + row_off),
+                                  adv->wrapx, 1, adv->decay, adv->imgs[adv->cur] + (size_t)y0 * adv->width, adv->imgs[dst] + (size_t)y0 * adv->width);
+            ctx->stream = main_stream;
+            if (rc) return rc;
+            adv->cur = dst;
+        }
     }
-    if (sink) {
-        int rc = enqueue_frame_copies(adv, ready, slot, nf, sink);
-        if (rc) return rc;
-    }
-    adv->simframe += nf;
-    adv->frames_since_regroup += nf;
-    if (adv->regroup_every && adv->frames_since_regroup >= adv->regroup_every) return regroup_points(adv);
+    rt.set_used[prev] = 0;
+    rt.set_used[set] = (int)nf;
+    adv->cur = slot[nf - 1];
+    CK(cudaEventRecord(rt.composited[set], side));
+    rt.composited_pending[set] = overlap;
+    if (ev) CK(cudaEventRecord(ev->c1, side));
+    if (overlap) adv->side_dirty = true;
+    if (sink) return enqueue_frame_copies(adv, rt.composited[set], slot, nf, sink);
     return CLUMPY_OK;
 }
 
@@ -1279,18 +1318,58 @@ static int route_steps_impl(clumpy_advect* adv, uint32_t count, RecordSink* sink
     REQUIRE(!adv->count_open, "advect_route_steps inside an open frame");
     int rc = route_check(adv);
     if (rc) return rc;
-    CK(cudaSetDevice(adv->ctx->device));
+    clumpy_cuda_ctx* ctx = adv->ctx;
+    CK(cudaSetDevice(ctx->device));
     auto& rt = adv->route;
     for (int r = 0; r < rt.world; ++r) REQUIRE(rt.peer_inbox[r], "peer inboxes are not mapped (route_peers)");
+    const bool overlap = adv->overlap && (!ev || ev->keep_overlap);
+    const bool pipelined = overlap && !ev && adv->npts > 0 && rt.pipeline;
+    RouteBack waiting[2]; // groups whose route kernel is enqueued and whose receiving half is not, oldest first
+    int nwaiting = 0;
+    auto flush = [&]() -> int {
+        for (int i = 0; i < nwaiting; ++i) {
+            const int e = route_back(adv, waiting[i], false, overlap, sink, ev);
+            if (e) return e;
+        }
+        nwaiting = 0;
+        return CLUMPY_OK;
+    };
     for (uint32_t i = 0; i < count;) {
         // a group never crosses a regroup or the warm-up / recording boundary (every rank cuts its groups at
         // the same frames: the group structure is part of the protocol)
         const uint32_t nf = advect_group_size(adv, count - i, rt.fuse);
-        rc = route_group(adv, nf, sink, ev);
+        const bool splat = frame_splats(adv);
+        if (!splat || !pipelined) { rc = flush(); if (rc) return rc; }
+        const bool carry = splat && pipelined && nwaiting == 2;
+        RouteBack mine;
+        rc = route_front(adv, nf, carry ? &waiting[0] : nullptr, ev, &mine);
         if (rc) return rc;
+        if (carry) {
+            rc = route_back(adv, waiting[0], true, overlap, sink, ev);
+            if (rc) return rc;
+            waiting[0] = waiting[1];
+            nwaiting = 1;
+        }
+        if (mine.nf) {
+            waiting[nwaiting++] = mine;
+            if (!pipelined) { rc = flush(); if (rc) return rc; }
+        } else {
+            // a group that does not splat leaves the framebuffer as it is
+            if (ev) for (cudaEvent_t e : {ev->d0, ev->d1, ev->c1}) CK(cudaEventRecord(e, ctx->stream));
+            if (sink) {
+                int slot[ADVECT_MAX_FUSE];
+                for (uint32_t f = 0; f < nf; ++f) slot[f] = adv->cur;
+                CK(cudaEventRecord(adv->frames_ready, overlap ? ctx->aux_stream : ctx->stream));
+                rc = enqueue_frame_copies(adv, adv->frames_ready, slot, nf, sink);
+                if (rc) return rc;
+            }
+        }
         i += nf;
         if (ev) break; // profiling: one group per call
     }
+    rc = flush();
+    if (rc) return rc;
+    if (ev && ev->keep_overlap) return CLUMPY_OK; // (the profiler joins once, at its end)
     return advect_join(adv); // whatever the caller enqueues next sees the finished framebuffer
 }
 
@@ -1323,11 +1402,16 @@ CLUMPY_API int clumpy_cuda_advect_route_profile(clumpy_advect* adv, uint32_t gro
             *p = nullptr;
             if (rc == CLUMPY_OK && cudaEventCreate(p) != cudaSuccess) { set_error("event creation failed"); rc = CLUMPY_ERR_CUDA; }
         }
+    // CLUMPY_ROUTE_TIMELINE=1 (development aid): leave the two streams as they run in production and print where
+    // every launch sat; the three means then overlap each other and do not add up to the step
+    const bool timeline = env_int("CLUMPY_ROUTE_TIMELINE", 0) == 1;
+    for (auto& e : ev) e.keep_overlap = timeline;
     std::vector<uint32_t> nfs(groups, 0);
     for (uint32_t g = 0; rc == CLUMPY_OK && g < groups; ++g) {
         nfs[g] = frame_splats(adv) ? advect_group_size(adv, (uint32_t)adv->route.fuse, adv->route.fuse) : 0u; // 0: not counted
         rc = route_steps_impl(adv, (uint32_t)adv->route.fuse, nullptr, &ev[g]);
     }
+    if (rc == CLUMPY_OK && timeline) rc = advect_join(adv);
     if (rc == CLUMPY_OK && cudaStreamSynchronize(adv->ctx->stream) != cudaSuccess) { set_error("profile run failed"); rc = CLUMPY_ERR_CUDA; }
     double t[3] = {0, 0, 0};
     uint32_t counted = 0;
@@ -1338,6 +1422,16 @@ CLUMPY_API int clumpy_cuda_advect_route_profile(clumpy_advect* adv, uint32_t gro
         cudaEventElapsedTime(&ms, ev[g].d0, ev[g].d1); t[1] += ms;
         cudaEventElapsedTime(&ms, ev[g].d1, ev[g].c1); t[2] += ms;
         ++counted;
+    }
+    if (rc == CLUMPY_OK && timeline) {
+        // development aid: where every launch of the last groups sat on this rank's clock (us since the first event)
+        for (uint32_t g = groups > 6 ? groups - 6 : 0; g < groups; ++g) {
+            float at[5] = {0, 0, 0, 0, 0};
+            const cudaEvent_t es[5] = {ev[g].r0, ev[g].r1, ev[g].d0, ev[g].d1, ev[g].c1};
+            for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&at[i], ev[0].r0, es[i]);
+            fprintf(stderr, "[timeline rank %d group %u nf %u] route %.0f..%.0f  drain %.0f..%.0f  composite ..%.0f us\n", adv->route.rank, g,
+                    nfs[g], at[0] * 1e3, at[1] * 1e3, at[2] * 1e3, at[3] * 1e3, at[4] * 1e3);
+        }
     }
     for (auto& e : ev) for (cudaEvent_t p : {e.r0, e.r1, e.d0, e.d1, e.c1}) if (p) cudaEventDestroy(p);
     if (route_ms) *route_ms = counted ? (float)(t[0] / counted) : 0.f;

@@ -178,8 +178,8 @@ constexpr int ROUTE_MAX_WORLD = 8;
 constexpr uint32_t ROUTE_BLOCK = ADVECT_THREADS * ADVECT_PTS; // points per CTA
 constexpr uint32_t ROUTE_REGION = ROUTE_BLOCK;                // entry slots per (CTA, destination, frame)
 constexpr int ROUTE_MAX_FUSE = ADVECT_MAX_FUSE;               // frames per launch
-constexpr int ROUTE_PARITIES = 4; // inbox slot sets in flight (see route_launch for why 4 is enough)
-constexpr int ROUTE_SETS = 3;     // band-buffer sets: counted into | composited | being zeroed
+constexpr int ROUTE_PARITIES = 8; // inbox slot sets in flight (see route_front in advect.cu for why 8 is enough)
+constexpr int ROUTE_SETS = 5;     // band-buffer sets: counted into | two waiting for their drain | composited | being zeroed
 
 struct RouteDev {
     int me, world;
@@ -242,6 +242,103 @@ __device__ __forceinline__ void route_cell(const RouteDev& rt, int f, uint32_t* 
     }
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// The receiving half of a group: once every source has published the group's epoch, the entries of every frame
+// of the group are counted into that frame's band buffer, one warp per (frame, source, region).  Count words are
+// zeroed as they are used: senders only ever write non-zero ones.
+struct DrainDev {
+    const uint32_t* inbox;      // this group's parity: [frame][source][region][ROUTE_REGION]
+    uint32_t* cnt;              // [frame][source][region]
+    size_t inbox_frame_stride, cnt_frame_stride;
+    uint32_t nregion;
+    int world, nf;              // nf == 0: nothing to count (the kernel only waits)
+    const uint32_t* flags;      // [source]; NULL: do not wait
+    uint32_t epoch;
+    uint32_t* errors;
+    unsigned long long timeout_ns;
+    uint32_t* band[ROUTE_MAX_FUSE];
+    uint32_t band_cells;
+    int wrap_w, halo, pitch;    // x-wrap mode: image width (else 0); band geometry
+};
+
+// Warp `warp` of `nwarp`'s share of the group.  The (frame, region) pairs are dealt to the warps ROUND-ROBIN (pair
+// p goes to warp p % nwarp): the non-empty regions are the CTAs near a band edge, which are neighbours in region
+// order, so a contiguous deal would leave all the work to a few warps.  A warp loads the count words of up to
+// 32 of its pairs in one go (most are zero: far CTAs send nothing), then works through the non-empty ones.
+template <int CELLS>
+__device__ __forceinline__ void drain_share(const DrainDev& d, uint32_t warp, uint32_t nwarp, uint32_t lane) {
+    const uint32_t per_frame = (uint32_t)d.world * d.nregion; // the count words of a frame are contiguous
+    const uint32_t total = per_frame * (uint32_t)d.nf;
+    for (uint32_t k0 = 0; warp + k0 * nwarp < total; k0 += 32u) {
+        const uint32_t pair = warp + (k0 + lane) * nwarp;
+        const uint32_t pf = pair < total ? pair / per_frame : 0u, pc = pair - pf * per_frame;
+        uint32_t* word = d.cnt + (size_t)pf * d.cnt_frame_stride + pc;
+        const uint32_t mine = (pair < total) ? min(__ldcg(word), ROUTE_REGION) : 0u; // written by a peer: read at L2
+        if (mine) *word = 0u;
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, mine != 0u);
+        while (todo) {
+            const int r = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t n = __shfl_sync(0xFFFFFFFFu, mine, r);
+            const uint32_t f = __shfl_sync(0xFFFFFFFFu, pf, r), c = __shfl_sync(0xFFFFFFFFu, pc, r);
+            const uint32_t* seg = d.inbox + (size_t)f * d.inbox_frame_stride + (size_t)c * ROUTE_REGION;
+            uint32_t* band = d.band[f];
+            for (uint32_t i0 = 0; i0 < n; i0 += 256u) { // 8 loads in flight per lane: the loop is latency-bound
+                uint32_t e[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t i = i0 + (uint32_t)j * 32u + lane;
+                    e[j] = i < n ? __ldcg(seg + i) : 0xFFFFFFFFu;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (e[j] >= d.band_cells) continue;
+                    band_add(band, e[j], CELLS == CELL_F16, d.wrap_w, d.halo, d.pitch);
+                }
+            }
+        }
+    }
+}
+
+// The stand-alone form: a launch that first waits for the epochs (bounded: on a time-out it records the error and
+// does nothing else -- the host turns a non-zero error count into a failed call), then counts.  With d.nf == 0
+// and one CTA it is the wait alone: the launch in front of a route kernel that carries the counting (see
+// advect_route_kernel), so that no CTA of that big grid ever sits on an SM waiting for a peer.
+template <int CELLS>
+__global__ void __launch_bounds__(256)
+drain_group_kernel(DrainDev d) {
+    if (d.flags) {
+        __shared__ int arrived;
+        if (threadIdx.x == 0) {
+            const unsigned long long t0 = globaltimer_ns();
+            int ok = 1;
+            for (int s = 0; s < d.world && ok; ++s) {
+                // epochs only grow; compare as signed distance so that wrap-around stays harmless.  The
+                // acquire load orders the reads of the entries (by the whole CTA, after the barrier) behind it.
+                while ((int32_t)(ld_acquire_sys(d.flags + s) - d.epoch) < 0) {
+                    __nanosleep(100);
+                    if (globaltimer_ns() - t0 > d.timeout_ns) { ok = 0; break; }
+                }
+            }
+            if (!ok && blockIdx.x == 0) atomicAdd(d.errors, 1u);
+            arrived = ok;
+        }
+        __syncthreads();
+        if (!arrived) return;
+    }
+    drain_share<CELLS>(d, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), gridDim.x * (blockDim.x >> 5), threadIdx.x & 31u);
+}
+
 // The group fence, sender side.  Called by every CTA after a barrier that follows its last remote store:
 // thread 0's fence.sys is cumulative over the stores of the whole CTA (they happen-before it through the
 // barrier); the ticket orders the CTAs; the last one fences again and publishes.
@@ -265,7 +362,7 @@ template <bool WRAP, bool SPLAT, bool F16, typename OffT, int MINB>
 __global__ void __launch_bounds__(ADVECT_THREADS, MINB)
 advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                     const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
-                    uint32_t width, uint32_t height, float step, GeomDev g, RouteDev rt) {
+                    uint32_t width, uint32_t height, float step, GeomDev g, RouteDev rt, DrainDev carried) {
     __shared__ uint32_t cta_n[ROUTE_MAX_FUSE][ROUTE_MAX_WORLD];
     if (SPLAT) {
         if (threadIdx.x < ROUTE_MAX_FUSE * ROUTE_MAX_WORLD) (&cta_n[0][0])[threadIdx.x] = 0u;
@@ -364,6 +461,12 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
     }
     const bool cta_sent = __syncthreads_or(n != 0u) != 0;
     route_group_fence(rt, cta_sent);
+    // The receiving half of an EARLIER group rides on this launch (carried.nf > 0): its entries arrived while the
+    // launches in between ran (the wait launch in front of this one saw the epochs), and counting them is a few
+    // loads and reductions per warp that hide among the resident CTAs -- as a launch of its own on the side stream
+    // the same work waited for SM slots behind this grid (2-GPU timeline, round 2: 105 us instead of 40).
+    if (carried.nf > 0)
+        drain_share<F16 ? CELL_F16 : CELL_U32>(carried, blockIdx.x * (ADVECT_THREADS >> 5) + (threadIdx.x >> 5), gridDim.x * (ADVECT_THREADS >> 5), threadIdx.x & 31u);
 }
 
 // The same fence for a rank that has no points this run (no route kernel to carry it).
@@ -371,97 +474,6 @@ __global__ void route_signal_kernel(RouteDev rt) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         __threadfence_system();
         for (int d = 0; d < rt.world; ++d) *reinterpret_cast<volatile uint32_t*>(rt.flags[d] + (rt.loopback ? d : rt.me)) = rt.epoch;
-    }
-}
-
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
-// The receiving half of a group: waits until every source has published the group's epoch (bounded: on a
-// time-out it records the error and does nothing else -- the host turns a non-zero error count into a failed
-// call), then counts the entries of every frame of the group into that frame's band buffer: one warp per
-// (frame, source, region).  Count words are zeroed as they are used: senders only ever write non-zero ones.
-struct DrainDev {
-    const uint32_t* inbox;      // this group's parity: [frame][source][region][ROUTE_REGION]
-    uint32_t* cnt;              // [frame][source][region]
-    size_t inbox_frame_stride, cnt_frame_stride;
-    uint32_t nregion;
-    int world, nf;
-    const uint32_t* flags;      // [source]; NULL: do not wait
-    uint32_t epoch;
-    uint32_t* errors;
-    unsigned long long timeout_ns;
-    uint32_t* band[ROUTE_MAX_FUSE];
-    uint32_t band_cells;
-    int wrap_w, halo, pitch;    // x-wrap mode: image width (else 0); band geometry
-};
-
-template <int CELLS>
-__global__ void __launch_bounds__(256)
-drain_group_kernel(DrainDev d) {
-    if (d.flags) {
-        __shared__ int arrived;
-        if (threadIdx.x == 0) {
-            const unsigned long long t0 = globaltimer_ns();
-            int ok = 1;
-            for (int s = 0; s < d.world && ok; ++s) {
-                // epochs only grow; compare as signed distance so that wrap-around stays harmless.  The
-                // acquire load orders the reads of the entries (by the whole CTA, after the barrier) behind it.
-                while ((int32_t)(ld_acquire_sys(d.flags + s) - d.epoch) < 0) {
-                    __nanosleep(100);
-                    if (globaltimer_ns() - t0 > d.timeout_ns) { ok = 0; break; }
-                }
-            }
-            if (!ok && blockIdx.x == 0) atomicAdd(d.errors, 1u);
-            arrived = ok;
-        }
-        __syncthreads();
-        if (!arrived) return;
-    }
-    // The (frame, region) pairs of the group are dealt to the warps ROUND-ROBIN (pair p goes to warp p % nwarp): the
-    // non-empty regions are the CTAs near a band edge, which are neighbours in region order, so a contiguous deal
-    // would leave all the work to a few warps.  A warp loads the count words of up to 32 of its pairs in one go
-    // (most are zero: far CTAs send nothing), then works through the non-empty ones.
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarp = gridDim.x * (blockDim.x >> 5);
-    const uint32_t per_frame = (uint32_t)d.world * d.nregion; // the count words of a frame are contiguous
-    const uint32_t total = per_frame * (uint32_t)d.nf;
-    for (uint32_t k0 = 0; warp + k0 * nwarp < total; k0 += 32u) {
-        const uint32_t pair = warp + (k0 + lane) * nwarp;
-        const uint32_t pf = pair < total ? pair / per_frame : 0u, pc = pair - pf * per_frame;
-        uint32_t* word = d.cnt + (size_t)pf * d.cnt_frame_stride + pc;
-        const uint32_t mine = (pair < total) ? min(__ldcg(word), ROUTE_REGION) : 0u; // written by a peer: read at L2
-        if (mine) *word = 0u;
-        uint32_t todo = __ballot_sync(0xFFFFFFFFu, mine != 0u);
-        while (todo) {
-            const int r = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            const uint32_t n = __shfl_sync(0xFFFFFFFFu, mine, r);
-            const uint32_t f = __shfl_sync(0xFFFFFFFFu, pf, r), c = __shfl_sync(0xFFFFFFFFu, pc, r);
-            const uint32_t* seg = d.inbox + (size_t)f * d.inbox_frame_stride + (size_t)c * ROUTE_REGION;
-            uint32_t* band = d.band[f];
-            for (uint32_t i0 = 0; i0 < n; i0 += 256u) { // 8 loads in flight per lane: the loop is latency-bound
-                uint32_t e[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t i = i0 + (uint32_t)j * 32u + lane;
-                    e[j] = i < n ? __ldcg(seg + i) : 0xFFFFFFFFu;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (e[j] >= d.band_cells) continue;
-                    band_add(band, e[j], CELLS == CELL_F16, d.wrap_w, d.halo, d.pitch);
-                }
-            }
-        }
     }
 }
 
