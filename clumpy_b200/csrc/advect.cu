@@ -148,7 +148,6 @@ struct clumpy_advect {
         unsigned long long timeout_ns = 2000000000ull;
         uint32_t epoch = 0;          // epoch of the last group launched
         bool loopback = false;       // CLUMPY_ROUTE_LOOPBACK=1: see route_begin
-        bool pipeline = true;        // the drain of a group rides on a later route launch (CLUMPY_ROUTE_PIPELINE=0: never)
     } route;
 };
 
@@ -976,7 +975,7 @@ static uint32_t* route_band(const clumpy_advect* adv, int set, int f) {
 }
 
 template <bool WRAP, bool SPLAT, bool F16, typename OffT>
-static void launch_route_t(clumpy_advect* a, const RouteDev& rd, const DrainDev& carried) {
+static void launch_route_t(clumpy_advect* a, const RouteDev& rd) {
     const uint32_t grid = ceil_div(a->npts, ROUTE_BLOCK); // CTA c owns region c of its segments
     const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch, a->keep_pos ? 1 : 0, 0};
     // CLUMPY_ROUTE_SMEM_KB=<n> (A/B): n KB of unused dynamic shared memory per CTA, to cap how many CTAs of this
@@ -984,10 +983,10 @@ static void launch_route_t(clumpy_advect* a, const RouteDev& rd, const DrainDev&
     const size_t pad = (size_t)std::min(std::max(env_int("CLUMPY_ROUTE_SMEM_KB", 0), 0), 48) * 1024;
     if (a->route.minb == 8)
         advect_route_kernel<WRAP, SPLAT, F16, OffT, 8><<<grid, ADVECT_THREADS, pad, a->ctx->stream>>>(
-            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd, carried);
+            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);
     else
         advect_route_kernel<WRAP, SPLAT, F16, OffT, 6><<<grid, ADVECT_THREADS, pad, a->ctx->stream>>>(
-            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd, carried);
+            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);
 }
 
 static size_t route_inbox_layout(uint32_t capacity, int world, uint32_t* nregion, size_t* entries_per_frame, size_t* cnt_per_frame,
@@ -1102,7 +1101,6 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     // publishes all `world` epochs into its own flags.  Timing and memory traffic are about those of a
     // real rank, the FRAMES ARE NOT (entries for other bands pile up in this rank's inbox).
     rt.loopback = env_int("CLUMPY_ROUTE_LOOPBACK", 0) == 1;
-    rt.pipeline = env_int("CLUMPY_ROUTE_PIPELINE", 1) != 0;
     rt.on = true;
     *inbox_dev = rt.inbox;
     if (rt.inbox_owned) *inbox_bytes = ibytes;
@@ -1124,38 +1122,34 @@ struct RouteEvents { cudaEvent_t r0, r1, d0, d1, c1; bool keep_overlap = false; 
 //   route_front   main stream: advect_route_kernel -- Euler step + reset of this rank's points through the group;
 //                 own-band points are counted into band buffer (set, f), the others' cells are stored into their
 //                 owners' inboxes (parity); at its end the group's epoch goes to every peer
-//   route_back    the entries the peers sent are counted into the band buffers (the "drain"), then the group
-//                 composite of this rank's image rows runs on the side stream; it also zeroes the band buffers of
-//                 the group before
+//   route_back    side stream: drain_group_kernel (waits for every peer's epoch, counts the inbox into the band
+//                 buffers), then the group composite of this rank's image rows, which also zeroes the band buffers
+//                 of the group before
 //
-// Inside one call the two halves are PIPELINED (route_steps_impl): the drain of group G rides on the route launch
-// of group G + 2 (`carried`), behind a one-CTA launch that waits for the peers' epochs G -- which by then have been
-// out for a whole group, so the ranks only pace each other loosely -- and composite(G) follows that launch on the
-// side stream, beside route(G + 3).  The groups still in flight at the end of a call (and every group of a profiled
-// or non-overlapping run) take the stand-alone form: drain_group_kernel (wait + count) and the composite.
-// Before round 2's last change every drain was such a launch on the side stream; the timeline (CLUMPY_ROUTE_TIMELINE)
-// showed it starved of SM slots by the route grid beside it (105 us instead of 40) and the route launches gated by
-// the side stream.
+// What may be reused when (G = this group; "its" = this rank's):
+//   band set G % 3 was read by composite(G - 3) and zeroed by composite(G - 2): the route launch waits for
+//     its composite(G - 2);
+//   inbox parity G % 4 was last written for group G - 4 and read by the PEERS' drain(G - 4).  Its composite(G - 2)
+//     is behind its drain(G - 2), which saw every peer's epoch G - 2, i.e. every peer's route(G - 2) had
+//     run, which that peer launched behind ITS composite(G - 4) and therefore behind its drain(G - 4).  So the
+//     same wait covers the inbox: four parities are enough and no peer is ever waited for on the host.
 //
-// What may be reused when (G = this group; "its" = this rank's; ROUTE_SETS = 5, ROUTE_PARITIES = 8):
-//   band set G % 5 was read by composite(G - 5) and zeroed by composite(G - 4): route(G) waits for its
-//     composite(G - 4), which was enqueued behind route(G - 2) at the latest -- so the wait never holds route(G)
-//     back behind route(G - 1), the launch in front of it, as it did with three and four sets;
-//   inbox parity G % 8 was last written for group G - 8 and read by the PEERS' drain(G - 8), carried or not.  Its
-//     composite(G - 4) is behind its drain(G - 4), which ran behind a wait for every peer's epoch G - 4: every
-//     peer's route(G - 4) had started, which that peer launched behind ITS composite(G - 8) and therefore behind
-//     its drain(G - 8).  So the same wait covers the inbox, in any mix of pipelined and stand-alone groups: eight
-//     parities are enough and no peer is ever waited for on the host.
+// Measured and dropped in round 2 (2 ranks on a quarter of C4 = the per-rank load of 8 GPUs; CLUMPY_ROUTE_TIMELINE
+// prints where the launches sit): more band sets and parities, so that route(G) no longer waits for composite(G - 2)
+// -- 0.0193 ms per frame, the same; the drain of group G riding on route(G + 2) behind a one-CTA wait launch, with
+// the composite alone on the side stream -- 0.0205 (20 frames: 0.0197 against 0.0174).  The three launches of a
+// group cost 95 + 40 + 57 us alone and about 150 us together however they are interleaved: the SMs are shared,
+// not idle.
 struct RouteBack { uint32_t nf = 0; int set = 0, parity = 0; uint32_t epoch = 0; };
 
-static DrainDev route_drain_desc(const clumpy_advect* adv, const RouteBack& b, bool wait) {
+static DrainDev route_drain_desc(const clumpy_advect* adv, const RouteBack& b) {
     const auto& rt = adv->route;
     DrainDev dd = {};
     dd.inbox = rt.inbox + (size_t)b.parity * ROUTE_MAX_FUSE * rt.entries_per_frame;
     dd.cnt = rt.inbox + rt.cnt_offset + (size_t)b.parity * ROUTE_MAX_FUSE * rt.cnt_per_frame;
     dd.inbox_frame_stride = rt.entries_per_frame; dd.cnt_frame_stride = rt.cnt_per_frame;
     dd.nregion = rt.nregion; dd.world = rt.world; dd.nf = (int)b.nf;
-    dd.flags = wait ? rt.inbox + rt.flags_offset : nullptr;
+    dd.flags = rt.inbox + rt.flags_offset;
     dd.epoch = b.epoch; dd.errors = rt.errors_dev; dd.timeout_ns = rt.timeout_ns;
     for (uint32_t f = 0; f < b.nf; ++f) dd.band[f] = route_band(adv, b.set, (int)f);
     dd.band_cells = rt.band_cells;
@@ -1163,16 +1157,15 @@ static DrainDev route_drain_desc(const clumpy_advect* adv, const RouteBack& b, b
     return dd;
 }
 
-// The sending half.  `carried`: an earlier group whose entries this launch counts on its way out (or NULL).
-// *back describes this group's receiving half (nf == 0: the group does not splat, nothing to receive).
-static int route_front(clumpy_advect* adv, uint32_t nf, const RouteBack* carried, RouteEvents* ev, RouteBack* back) {
+// The sending half.  *back describes this group's receiving half (nf == 0: the group does not splat, nothing to receive).
+static int route_front(clumpy_advect* adv, uint32_t nf, RouteEvents* ev, RouteBack* back) {
     clumpy_cuda_ctx* ctx = adv->ctx;
     auto& rt = adv->route;
     const bool splat = frame_splats(adv);
     const cudaStream_t main_stream = ctx->stream;
     const int set = (int)(rt.group_index % RSETS), parity = (int)(rt.group_index % ROUTE_PARITIES);
     if (splat) {
-        const int z = (set + 1) % RSETS; // the set of group G - 4, whose composite zeroed the set of group G - 5: this one
+        const int z = (set + 1) % RSETS; // the set of group G - 2, whose composite zeroed the set of group G - 3: this one
         if (rt.composited_pending[z]) {
             CK(cudaStreamWaitEvent(main_stream, rt.composited[z], 0));
             rt.composited_pending[z] = false;
@@ -1197,27 +1190,15 @@ static int route_front(clumpy_advect* adv, uint32_t nf, const RouteBack* carried
         rd.cnt[r] = rt.peer_inbox[r] + rt.cnt_offset;
         rd.flags[r] = rt.peer_inbox[r] + rt.flags_offset;
     }
-    DrainDev carry = {};
-    if (carried) {
-        // the wait alone, one CTA: the peers' epochs of the carried group (bounded; a time-out is recorded and the
-        // counting goes ahead on whatever arrived -- the host fails the call on the error count)
-        RouteBack none = *carried;
-        none.nf = 0;
-        const DrainDev wd = route_drain_desc(adv, none, true);
-        if (adv->cell_mode == CELL_F16) drain_group_kernel<CELL_F16><<<1, 32, 0, main_stream>>>(wd);
-        else drain_group_kernel<CELL_U32><<<1, 32, 0, main_stream>>>(wd);
-        CK_LAUNCH(ctx);
-        carry = route_drain_desc(adv, *carried, false);
-    }
     if (ev) CK(cudaEventRecord(ev->r0, main_stream));
     if (adv->npts) {
-#define ROUTE_LAUNCH(W, S) (adv->cell_mode == CELL_F16 ? (adv->off16 ? launch_route_t<W, S, true, uint16_t>(adv, rd, carry) : launch_route_t<W, S, true, uint32_t>(adv, rd, carry)) \
-                                                       : (adv->off16 ? launch_route_t<W, S, false, uint16_t>(adv, rd, carry) : launch_route_t<W, S, false, uint32_t>(adv, rd, carry)))
+#define ROUTE_LAUNCH(W, S) (adv->cell_mode == CELL_F16 ? (adv->off16 ? launch_route_t<W, S, true, uint16_t>(adv, rd) : launch_route_t<W, S, true, uint32_t>(adv, rd)) \
+                                                       : (adv->off16 ? launch_route_t<W, S, false, uint16_t>(adv, rd) : launch_route_t<W, S, false, uint32_t>(adv, rd)))
         if (adv->wrapx) { if (splat) ROUTE_LAUNCH(true, true); else ROUTE_LAUNCH(true, false); }
         else            { if (splat) ROUTE_LAUNCH(false, true); else ROUTE_LAUNCH(false, false); }
 #undef ROUTE_LAUNCH
         CK_LAUNCH(ctx);
-    } else if (splat) { // no route kernel to carry the fence (and nothing is ever carried: see route_steps_impl)
+    } else if (splat) { // no route kernel to carry the fence
         route_signal_kernel<<<1, 32, 0, main_stream>>>(rd);
         CK_LAUNCH(ctx);
     }
@@ -1234,8 +1215,8 @@ static int route_front(clumpy_advect* adv, uint32_t nf, const RouteBack* carried
     return CLUMPY_OK;
 }
 
-// The receiving half of group `b` (in group order).  `counted`: a route launch already carried the drain.
-static int route_back(clumpy_advect* adv, const RouteBack& b, bool counted, bool overlap, RecordSink* sink, RouteEvents* ev) {
+// The receiving half of group `b`.
+static int route_back(clumpy_advect* adv, const RouteBack& b, bool overlap, RecordSink* sink, RouteEvents* ev) {
     clumpy_cuda_ctx* ctx = adv->ctx;
     auto& rt = adv->route;
     const cudaStream_t main_stream = ctx->stream;
@@ -1244,15 +1225,14 @@ static int route_back(clumpy_advect* adv, const RouteBack& b, bool counted, bool
     const int set = b.set;
     int slot[ADVECT_MAX_FUSE];
     if (overlap) {
-        // behind the launches of the main stream so far: this rank's own counts of the group and (counted) the
-        // route launch that carried its drain; a stand-alone drain that started earlier would only sit on SM
-        // slots waiting for this rank's own epoch
+        // the receiving half starts once this rank's own route kernel is done (by then its own epoch is
+        // out; a drain that started earlier would only sit on SM slots waiting for it)
         CK(cudaEventRecord(rt.routed, main_stream));
         CK(cudaStreamWaitEvent(side, rt.routed, 0));
     }
     if (ev) CK(cudaEventRecord(ev->d0, side));
-    if (!counted) {
-        const DrainDev dd = route_drain_desc(adv, b, true);
+    {
+        const DrainDev dd = route_drain_desc(adv, b);
         // 16 (frame, region) pairs per warp; the CTAs wait (one thread each) for the peers' epochs before they work
         const uint32_t dgrid = std::min<uint32_t>((uint32_t)ctx->sm_count * 8u, std::max<uint32_t>(1u, ceil_div((uint32_t)(nf * rt.cnt_per_frame), 16u * 8u)));
         if (adv->cell_mode == CELL_F16) drain_group_kernel<CELL_F16><<<dgrid, 256, 0, side>>>(dd);
@@ -1322,37 +1302,18 @@ static int route_steps_impl(clumpy_advect* adv, uint32_t count, RecordSink* sink
     CK(cudaSetDevice(ctx->device));
     auto& rt = adv->route;
     for (int r = 0; r < rt.world; ++r) REQUIRE(rt.peer_inbox[r], "peer inboxes are not mapped (route_peers)");
-    const bool overlap = adv->overlap && (!ev || ev->keep_overlap);
-    const bool pipelined = overlap && !ev && adv->npts > 0 && rt.pipeline;
-    RouteBack waiting[2]; // groups whose route kernel is enqueued and whose receiving half is not, oldest first
-    int nwaiting = 0;
-    auto flush = [&]() -> int {
-        for (int i = 0; i < nwaiting; ++i) {
-            const int e = route_back(adv, waiting[i], false, overlap, sink, ev);
-            if (e) return e;
-        }
-        nwaiting = 0;
-        return CLUMPY_OK;
-    };
+    const bool keep_overlap = ev && ev->keep_overlap;
+    const bool overlap = adv->overlap && (!ev || keep_overlap);
     for (uint32_t i = 0; i < count;) {
         // a group never crosses a regroup or the warm-up / recording boundary (every rank cuts its groups at
         // the same frames: the group structure is part of the protocol)
         const uint32_t nf = advect_group_size(adv, count - i, rt.fuse);
-        const bool splat = frame_splats(adv);
-        if (!splat || !pipelined) { rc = flush(); if (rc) return rc; }
-        const bool carry = splat && pipelined && nwaiting == 2;
         RouteBack mine;
-        rc = route_front(adv, nf, carry ? &waiting[0] : nullptr, ev, &mine);
+        rc = route_front(adv, nf, ev, &mine);
         if (rc) return rc;
-        if (carry) {
-            rc = route_back(adv, waiting[0], true, overlap, sink, ev);
-            if (rc) return rc;
-            waiting[0] = waiting[1];
-            nwaiting = 1;
-        }
         if (mine.nf) {
-            waiting[nwaiting++] = mine;
-            if (!pipelined) { rc = flush(); if (rc) return rc; }
+            rc = route_back(adv, mine, overlap, sink, ev);
+            if (rc) return rc;
         } else {
             // a group that does not splat leaves the framebuffer as it is
             if (ev) for (cudaEvent_t e : {ev->d0, ev->d1, ev->c1}) CK(cudaEventRecord(e, ctx->stream));
@@ -1367,9 +1328,7 @@ static int route_steps_impl(clumpy_advect* adv, uint32_t count, RecordSink* sink
         i += nf;
         if (ev) break; // profiling: one group per call
     }
-    rc = flush();
-    if (rc) return rc;
-    if (ev && ev->keep_overlap) return CLUMPY_OK; // (the profiler joins once, at its end)
+    if (keep_overlap) return CLUMPY_OK; // (the timeline joins once, at its end)
     return advect_join(adv); // whatever the caller enqueues next sees the finished framebuffer
 }
 

@@ -175,11 +175,12 @@ advect_fused_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
 // the group's EPOCH into a flag per source in every peer's memory.  The receiver (drain_group_kernel) waits
 // for every source's epoch, counts the entries into its band buffers and zeroes the count words it used.
 constexpr int ROUTE_MAX_WORLD = 8;
-constexpr uint32_t ROUTE_BLOCK = ADVECT_THREADS * ADVECT_PTS; // points per CTA
+constexpr int ROUTE_PTS = 4;                                  // points per thread of the route kernel
+constexpr uint32_t ROUTE_BLOCK = ADVECT_THREADS * ROUTE_PTS;  // points per CTA
 constexpr uint32_t ROUTE_REGION = ROUTE_BLOCK;                // entry slots per (CTA, destination, frame)
 constexpr int ROUTE_MAX_FUSE = ADVECT_MAX_FUSE;               // frames per launch
-constexpr int ROUTE_PARITIES = 8; // inbox slot sets in flight (see route_front in advect.cu for why 8 is enough)
-constexpr int ROUTE_SETS = 5;     // band-buffer sets: counted into | two waiting for their drain | composited | being zeroed
+constexpr int ROUTE_PARITIES = 4; // inbox slot sets in flight (see route_front in advect.cu for why 4 is enough)
+constexpr int ROUTE_SETS = 3;     // band-buffer sets: counted into | composited | being zeroed
 
 struct RouteDev {
     int me, world;
@@ -261,7 +262,7 @@ struct DrainDev {
     uint32_t* cnt;              // [frame][source][region]
     size_t inbox_frame_stride, cnt_frame_stride;
     uint32_t nregion;
-    int world, nf;              // nf == 0: nothing to count (the kernel only waits)
+    int world, nf;
     const uint32_t* flags;      // [source]; NULL: do not wait
     uint32_t epoch;
     uint32_t* errors;
@@ -310,10 +311,8 @@ __device__ __forceinline__ void drain_share(const DrainDev& d, uint32_t warp, ui
     }
 }
 
-// The stand-alone form: a launch that first waits for the epochs (bounded: on a time-out it records the error and
-// does nothing else -- the host turns a non-zero error count into a failed call), then counts.  With d.nf == 0
-// and one CTA it is the wait alone: the launch in front of a route kernel that carries the counting (see
-// advect_route_kernel), so that no CTA of that big grid ever sits on an SM waiting for a peer.
+// The launch: waits for the epochs first (bounded: on a time-out it records the error and does nothing else -- the
+// host turns a non-zero error count into a failed call), then counts.
 template <int CELLS>
 __global__ void __launch_bounds__(256)
 drain_group_kernel(DrainDev d) {
@@ -362,7 +361,7 @@ template <bool WRAP, bool SPLAT, bool F16, typename OffT, int MINB>
 __global__ void __launch_bounds__(ADVECT_THREADS, MINB)
 advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                     const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
-                    uint32_t width, uint32_t height, float step, GeomDev g, RouteDev rt, DrainDev carried) {
+                    uint32_t width, uint32_t height, float step, GeomDev g, RouteDev rt) {
     __shared__ uint32_t cta_n[ROUTE_MAX_FUSE][ROUTE_MAX_WORLD];
     if (SPLAT) {
         if (threadIdx.x < ROUTE_MAX_FUSE * ROUTE_MAX_WORLD) (&cta_n[0][0])[threadIdx.x] = 0u;
@@ -372,11 +371,11 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
     const uint32_t base = blockIdx.x * ROUTE_BLOCK + threadIdx.x;
     const int my_lo = rt.me * rt.chunk; // first padded row of this rank's band
     // positions and reset phases: loaded once for the whole group of frames
-    float2 p[ADVECT_PTS];
-    uint32_t off[ADVECT_PTS];
-    bool live[ADVECT_PTS];
+    float2 p[ROUTE_PTS];
+    uint32_t off[ROUTE_PTS];
+    bool live[ROUTE_PTS];
 #pragma unroll
-    for (int k = 0; k < ADVECT_PTS; ++k) {
+    for (int k = 0; k < ROUTE_PTS; ++k) {
         const uint32_t i = base + k * ADVECT_THREADS;
         live[k] = i < npts;
         p[k] = make_float2(0.f, 0.f);
@@ -388,18 +387,18 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
     }
     // each position is truncated once: the integers serve the splat of the frame that produced the position
     // (splat_points.cc:143-144) and the velocity fetch of the next frame (advect_points.cc:23-37)
-    int32_t tx[ADVECT_PTS], ty[ADVECT_PTS];
+    int32_t tx[ROUTE_PTS], ty[ROUTE_PTS];
 #pragma unroll
-    for (int k = 0; k < ADVECT_PTS; ++k) { tx[k] = __float2int_rz(p[k].x); ty[k] = __float2int_rz(p[k].y); }
+    for (int k = 0; k < ROUTE_PTS; ++k) { tx[k] = __float2int_rz(p[k].x); ty[k] = __float2int_rz(p[k].y); }
     // the rows of this rank's band that are out of the sprite's reach of its edges: a point that lands there
     // (most do) costs one reduction and none of the routing logic
     const uint32_t interior = (uint32_t)max(rt.chunk - 2 * rt.halo, 0);
     const uint32_t padded_w = (uint32_t)(g.width + 2 * g.halo), padded_h = (uint32_t)(g.height + 2 * g.halo);
     uint32_t phase = rt.phase0;
     for (int f = 0; f < rt.nf; ++f) {
-        float2 v[ADVECT_PTS];
+        float2 v[ROUTE_PTS];
 #pragma unroll
-        for (int k = 0; k < ADVECT_PTS; ++k) { // nearest-texel fetch (advect_points.cc:23-37)
+        for (int k = 0; k < ROUTE_PTS; ++k) { // nearest-texel fetch (advect_points.cc:23-37)
             uint32_t x = fetch_index(tx[k], p[k].x);
             const uint32_t y = fetch_index(ty[k], p[k].y);
             if (WRAP) x = (width + (x % width)) % width;
@@ -407,7 +406,7 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
             if (live[k] && x < width && y < height) v[k] = __ldg(vel + ((size_t)y * width + x));
         }
 #pragma unroll
-        for (int k = 0; k < ADVECT_PTS; ++k) {
+        for (int k = 0; k < ROUTE_PTS; ++k) {
             // pt += step * v: rounded multiply, then rounded add (:146)
             p[k] = make_float2(__fadd_rn(p[k].x, __fmul_rn(step, v[k].x)), __fadd_rn(p[k].y, __fmul_rn(step, v[k].y)));
             if (off[k] == phase) p[k] = orig[base + k * ADVECT_THREADS]; // reset AFTER the move (:147-152,166-170)
@@ -417,7 +416,7 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
         phase = phase + 1u == rt.nframes ? 0u : phase + 1u;
         uint32_t* const band = rt.band[f];
 #pragma unroll
-        for (int k = 0; SPLAT && k < ADVECT_PTS; ++k) {
+        for (int k = 0; SPLAT && k < ROUTE_PTS; ++k) {
             // splat_points.cc:143-144: centre texel by (int32_t) truncation; same tests as hist_index
             const int32_t cx = splat_index(tx[k], p[k].x), cy = splat_index(ty[k], p[k].y);
             const uint32_t uy = (uint32_t)cy + (uint32_t)g.halo;
@@ -448,7 +447,7 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
         }
     }
 #pragma unroll
-    for (int k = 0; k < ADVECT_PTS; ++k)
+    for (int k = 0; k < ROUTE_PTS; ++k)
         if (live[k]) st_stream_f2(pos + base + k * ADVECT_THREADS, p[k], pol);
     if (!SPLAT) return;
     __syncthreads(); // every entry of this CTA is written, cta_n is final
@@ -461,12 +460,6 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
     }
     const bool cta_sent = __syncthreads_or(n != 0u) != 0;
     route_group_fence(rt, cta_sent);
-    // The receiving half of an EARLIER group rides on this launch (carried.nf > 0): its entries arrived while the
-    // launches in between ran (the wait launch in front of this one saw the epochs), and counting them is a few
-    // loads and reductions per warp that hide among the resident CTAs -- as a launch of its own on the side stream
-    // the same work waited for SM slots behind this grid (2-GPU timeline, round 2: 105 us instead of 40).
-    if (carried.nf > 0)
-        drain_share<F16 ? CELL_F16 : CELL_U32>(carried, blockIdx.x * (ADVECT_THREADS >> 5) + (threadIdx.x >> 5), gridDim.x * (ADVECT_THREADS >> 5), threadIdx.x & 31u);
 }
 
 // The same fence for a rank that has no points this run (no route kernel to carry it).
