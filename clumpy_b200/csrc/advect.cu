@@ -1082,8 +1082,8 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
         dd.nregion = rt.nregion; dd.world = world; dd.nf = 1; dd.flags = nullptr; dd.errors = rt.errors_dev;
         dd.band[0] = rt.band; dd.band_cells = rt.band_cells;
         dd.wrap_w = 0; dd.halo = adv->geom.halo; dd.pitch = adv->geom.pitch;
-        if (adv->cell_mode == CELL_F16) drain_group_kernel<CELL_F16><<<1, 256, 0, ctx->stream>>>(dd);
-        else drain_group_kernel<CELL_U32><<<1, 256, 0, ctx->stream>>>(dd);
+        if (adv->cell_mode == CELL_F16) drain_group_kernel<CELL_F16><<<1, DRAIN_THREADS, 0, ctx->stream>>>(dd);
+        else drain_group_kernel<CELL_U32><<<1, DRAIN_THREADS, 0, ctx->stream>>>(dd);
         CK_LAUNCH(ctx);
         const int h = adv->geom.halo, lo = rank * rt.chunk;
         const int y0 = std::max(0, lo - h), y1 = route_last_row(adv);
@@ -1182,6 +1182,12 @@ static int route_front(clumpy_advect* adv, uint32_t nf, RouteEvents* ev, RouteBa
     rd.cnt_frame_stride = rt.cnt_per_frame;
     for (uint32_t f = 0; f < nf; ++f) rd.band[f] = route_band(adv, set, (int)f);
     rd.band_f16 = adv->cell_mode == CELL_F16 ? 1 : 0;
+    {
+        const int my_lo = rt.rank * rt.chunk, gh = adv->geom.halo;
+        rd.interior = (uint32_t)std::max(rt.chunk - 2 * rd.halo, 0);
+        rd.in_row0 = my_lo + rd.halo - gh;
+        rd.in_bias = (gh - my_lo + rd.halo) * rd.pitch + gh;
+    }
     rd.epoch = splat ? rt.epoch + 1u : rt.epoch;
     rd.loopback = rt.loopback ? 1 : 0;
     rd.ticket = rt.ticket;
@@ -1234,9 +1240,10 @@ static int route_back(clumpy_advect* adv, const RouteBack& b, bool overlap, Reco
     {
         const DrainDev dd = route_drain_desc(adv, b);
         // 16 (frame, region) pairs per warp; the CTAs wait (one thread each) for the peers' epochs before they work
-        const uint32_t dgrid = std::min<uint32_t>((uint32_t)ctx->sm_count * 8u, std::max<uint32_t>(1u, ceil_div((uint32_t)(nf * rt.cnt_per_frame), 16u * 8u)));
-        if (adv->cell_mode == CELL_F16) drain_group_kernel<CELL_F16><<<dgrid, 256, 0, side>>>(dd);
-        else drain_group_kernel<CELL_U32><<<dgrid, 256, 0, side>>>(dd);
+        constexpr uint32_t warps = DRAIN_THREADS / 32;
+        const uint32_t dgrid = std::min<uint32_t>((uint32_t)ctx->sm_count * 16u, std::max<uint32_t>(1u, ceil_div((uint32_t)(nf * rt.cnt_per_frame), 16u * warps)));
+        if (adv->cell_mode == CELL_F16) drain_group_kernel<CELL_F16><<<dgrid, DRAIN_THREADS, 0, side>>>(dd);
+        else drain_group_kernel<CELL_U32><<<dgrid, DRAIN_THREADS, 0, side>>>(dd);
         CK_LAUNCH(ctx);
     }
     if (ev) CK(cudaEventRecord(ev->d1, side));

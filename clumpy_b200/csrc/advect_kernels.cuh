@@ -199,6 +199,10 @@ struct RouteDev {
     int loopback;                       // profiling aid: every "peer" is this rank itself (see route_begin)
     uint32_t epoch;                     // epoch of the group
     uint32_t* ticket;                   // CTAs of this launch that are done
+    // the common case of a splat (see advect_route_kernel): image rows [in_row0, in_row0 + interior) of this rank's
+    // band are out of the sprite's reach of the band edges; cell index there = cy * pitch + cx + in_bias
+    int32_t in_row0, in_bias;
+    uint32_t interior;
 };
 
 // One count into a band buffer.  Half cells in x-wrap mode (wrap_w = image width, else 0): the group
@@ -313,8 +317,12 @@ __device__ __forceinline__ void drain_share(const DrainDev& d, uint32_t warp, ui
 
 // The launch: waits for the epochs first (bounded: on a time-out it records the error and does nothing else -- the
 // host turns a non-zero error count into a failed call), then counts.
+// DRAIN_THREADS x 32 registers = 4096: what an SM has left beside six CTAs of the route kernel (6 x 256 x 40), so the
+// drain of one group starts next to the route launch of the next instead of waiting for its CTAs to retire.
+constexpr int DRAIN_THREADS = 128;
+
 template <int CELLS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(DRAIN_THREADS)
 drain_group_kernel(DrainDev d) {
     if (d.flags) {
         __shared__ int arrived;
@@ -370,7 +378,9 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
     const uint64_t pol = g.keep_pos == 0 ? make_stream_policy() : make_normal_policy();
     const uint32_t base = blockIdx.x * ROUTE_BLOCK + threadIdx.x;
     const int my_lo = rt.me * rt.chunk; // first padded row of this rank's band
-    // positions and reset phases: loaded once for the whole group of frames
+    // positions and reset phases: loaded once for the whole group of frames.  A slot past the end of the shard gets
+    // a position that fails every test below by itself (no velocity texel, no cell, never reset), so the frame loop
+    // does not ask `live` again.
     float2 p[ROUTE_PTS];
     uint32_t off[ROUTE_PTS];
     bool live[ROUTE_PTS];
@@ -378,49 +388,84 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
     for (int k = 0; k < ROUTE_PTS; ++k) {
         const uint32_t i = base + k * ADVECT_THREADS;
         live[k] = i < npts;
-        p[k] = make_float2(0.f, 0.f);
+        p[k] = make_float2(-1.0e8f, -1.0e8f);
         off[k] = 0xFFFFFFFFu;
         if (live[k]) {
             p[k] = ld_stream_f2(pos + i, pol);
             off[k] = ld_stream_off(offset + i, pol);
         }
     }
-    // each position is truncated once: the integers serve the splat of the frame that produced the position
-    // (splat_points.cc:143-144) and the velocity fetch of the next frame (advect_points.cc:23-37)
+    // Each position is truncated once: the integers serve the splat of the frame that produced the position
+    // (splat_points.cc:143-144) and the velocity fetch of the next frame (advect_points.cc:23-37).  The two casts
+    // of the reference differ from the plain truncation only for |coordinate| >= 2^31 and NaN; `odd` says whether
+    // ANY coordinate of this thread is such a value (a sum of magnitudes: NaN and overflow propagate, and a sum of
+    // non-negative terms is never below its largest one), and only then are fetch_index / splat_index asked.
     int32_t tx[ROUTE_PTS], ty[ROUTE_PTS];
+    bool odd;
+    auto truncate = [&]() {
+        float mag = 0.f;
 #pragma unroll
-    for (int k = 0; k < ROUTE_PTS; ++k) { tx[k] = __float2int_rz(p[k].x); ty[k] = __float2int_rz(p[k].y); }
-    // the rows of this rank's band that are out of the sprite's reach of its edges: a point that lands there
-    // (most do) costs one reduction and none of the routing logic
-    const uint32_t interior = (uint32_t)max(rt.chunk - 2 * rt.halo, 0);
+        for (int k = 0; k < ROUTE_PTS; ++k) {
+            tx[k] = __float2int_rz(p[k].x);
+            ty[k] = __float2int_rz(p[k].y);
+            mag = __fadd_rn(mag, __fadd_rn(fabsf(p[k].x), fabsf(p[k].y)));
+        }
+        odd = !(mag < 2147483648.0f);
+    };
+    truncate();
+    // The common case of a splat -- the cell lies in this rank's own band, out of the sprite's reach of the band
+    // edges, inside the image -- is two compares, one multiply-add and the reduction: with c = (cx, cy) the centre
+    // texel, the test is in_row0 <= cy < in_row0 + interior and 0 <= cx < width, and the cell index in the band
+    // buffer ((r + halo) * pitch + ux in route_cell's terms) is cy * pitch + cx + in_bias (set by the host).
     const uint32_t padded_w = (uint32_t)(g.width + 2 * g.halo), padded_h = (uint32_t)(g.height + 2 * g.halo);
+    const char* const vel_bytes = reinterpret_cast<const char*>(vel);
+    const uint32_t vel_pitch = width * (uint32_t)sizeof(float2); // (a row of the field is below 4 GB)
     uint32_t phase = rt.phase0;
     for (int f = 0; f < rt.nf; ++f) {
+        uint32_t gx[ROUTE_PTS], gy[ROUTE_PTS];
+#pragma unroll
+        for (int k = 0; k < ROUTE_PTS; ++k) { gx[k] = (uint32_t)tx[k]; gy[k] = (uint32_t)ty[k]; }
+        if (odd) {
+#pragma unroll
+            for (int k = 0; k < ROUTE_PTS; ++k) { gx[k] = fetch_index(tx[k], p[k].x); gy[k] = fetch_index(ty[k], p[k].y); }
+        }
         float2 v[ROUTE_PTS];
 #pragma unroll
         for (int k = 0; k < ROUTE_PTS; ++k) { // nearest-texel fetch (advect_points.cc:23-37)
-            uint32_t x = fetch_index(tx[k], p[k].x);
-            const uint32_t y = fetch_index(ty[k], p[k].y);
+            uint32_t x = gx[k];
             if (WRAP) x = (width + (x % width)) % width;
             v[k] = make_float2(0.f, 0.f);
-            if (live[k] && x < width && y < height) v[k] = __ldg(vel + ((size_t)y * width + x));
+            if (x < width && gy[k] < height)
+                v[k] = __ldg(reinterpret_cast<const float2*>(vel_bytes + (uint64_t)gy[k] * vel_pitch + (uint64_t)x * sizeof(float2)));
         }
 #pragma unroll
         for (int k = 0; k < ROUTE_PTS; ++k) {
             // pt += step * v: rounded multiply, then rounded add (:146)
             p[k] = make_float2(__fadd_rn(p[k].x, __fmul_rn(step, v[k].x)), __fadd_rn(p[k].y, __fmul_rn(step, v[k].y)));
-            if (off[k] == phase) p[k] = orig[base + k * ADVECT_THREADS]; // reset AFTER the move (:147-152,166-170)
-            tx[k] = __float2int_rz(p[k].x);
-            ty[k] = __float2int_rz(p[k].y);
         }
+        bool reset = false; // one point in nframes per frame: a single branch for the thread's points
+#pragma unroll
+        for (int k = 0; k < ROUTE_PTS; ++k) reset |= off[k] == phase;
+        if (reset) {
+#pragma unroll
+            for (int k = 0; k < ROUTE_PTS; ++k)
+                if (off[k] == phase) p[k] = orig[base + k * ADVECT_THREADS]; // reset AFTER the move (:147-152,166-170)
+        }
+        truncate();
         phase = phase + 1u == rt.nframes ? 0u : phase + 1u;
         uint32_t* const band = rt.band[f];
 #pragma unroll
         for (int k = 0; SPLAT && k < ROUTE_PTS; ++k) {
+            if (!WRAP && !odd && (uint32_t)(ty[k] - rt.in_row0) < rt.interior && (uint32_t)tx[k] < (uint32_t)g.width) {
+                const uint32_t entry = (uint32_t)(ty[k] * rt.pitch + tx[k] + rt.in_bias);
+                if (F16) cell_add_f16(band, (long long)entry);
+                else atomicAdd(band + entry, 1u);
+                continue;
+            }
             // splat_points.cc:143-144: centre texel by (int32_t) truncation; same tests as hist_index
             const int32_t cx = splat_index(tx[k], p[k].x), cy = splat_index(ty[k], p[k].y);
             const uint32_t uy = (uint32_t)cy + (uint32_t)g.halo;
-            if (!live[k] || uy >= padded_h) continue;
+            if (uy >= padded_h) continue;
             uint32_t ux;
             if (WRAP) {
                 int32_t m = cx % g.width;
@@ -431,12 +476,6 @@ advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                 if (ux >= padded_w) continue;
             }
             int r = (int)uy - my_lo;
-            if (!WRAP && (uint32_t)(r - rt.halo) < interior && (uint32_t)cx < (uint32_t)g.width) { // own band, away from its edges, inside the image
-                const uint32_t entry = (uint32_t)((r + rt.halo) * rt.pitch) + ux;
-                if (F16) cell_add_f16(band, (long long)entry);
-                else atomicAdd(band + entry, 1u);
-                continue;
-            }
             int owner = rt.me;
             if ((uint32_t)r >= (uint32_t)rt.chunk) {
                 owner = min((int)(uy / (uint32_t)rt.chunk), rt.world - 1);
