@@ -11,7 +11,7 @@ ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := $(ARCH) -O3 -std=c++17 -lineinfo --expt-relaxed-constexpr -Iinclude \
             -Xcompiler -fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function $(EXTRA_NVFLAGS)
 CSRC     := clumpy_b200/csrc
-CUFILES  := $(CSRC)/context.cu $(CSRC)/simplex.cu $(CSRC)/curl.cu $(CSRC)/splat.cu $(CSRC)/splat_multi.cu \
+CUFILES  := $(CSRC)/context.cu $(CSRC)/simplex.cu $(CSRC)/curl.cu $(CSRC)/splat.cu $(CSRC)/splat_multi.cu $(CSRC)/age_offsets_dev.cu \
             $(CSRC)/composite_group.cu $(CSRC)/composite_exact.cu $(CSRC)/advect.cu $(CSRC)/advect_multi.cu $(CSRC)/producers.cu $(CSRC)/microbench.cu
 CUOBJS   := $(CUFILES:.cu=.o) $(CSRC)/age_offsets.o
 LIB      := clumpy_b200/libclumpy_cuda.so

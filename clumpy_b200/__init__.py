@@ -59,6 +59,7 @@ SIGNATURES = {
     "clumpy_cuda_splat_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                           C.c_float, C.c_int, C.c_int]),
     "clumpy_cuda_age_offsets": (C.c_int, [C.c_uint32, C.c_uint32, _u32p]),
+    "clumpy_cuda_age_offsets_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "clumpy_cuda_advect_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                            C.c_uint32, C.c_uint32, C.c_float, C.c_int, C.c_float,
                                            C.c_int, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -359,6 +360,10 @@ class Context:
             self._h, width, height, row0, nrows, amplitude, frequency, int(seed), _vp(out_dev),
             C.byref(lo) if want_range else None, C.byref(hi) if want_range else None))
         return (lo.value, hi.value) if want_range else None
+
+    def age_offsets_dev(self, nframes, npts, out_dev):
+        """`npts` reset offsets (advect_points.cc:127-135) drawn on the device into uint32 device memory."""
+        _check(lib().clumpy_cuda_age_offsets_dev(self._h, nframes, npts, _vp(out_dev)))
 
     def generate_simplex_octaves_dev(self, width, height, row0, nrows, amplitudes, frequencies, seeds, out_dev, want_range=False):
         """Rows [row0, row0 + nrows) of the FP32 sum of the octaves (amplitude, frequency, seed), in that order."""

@@ -365,21 +365,24 @@ static int advect_begin_impl(clumpy_advect* a, const clumpy_advect_desc& d) {
     for (int s = 0; s < NSETS; ++s) CK(cudaEventCreateWithFlags(&a->set_composited[s], cudaEventDisableTiming));
     for (int b = 0; b < LEGACY_RING; ++b) CK(cudaEventCreateWithFlags(&a->cleared[b], cudaEventDisableTiming));
 
-    // reset offsets: the caller's, or ours -- computed on a host thread while this thread allocates and uploads
+    // Reset offsets: the caller's, or ours.  Ours are drawn on the device (age_offsets_dev.cu: one CTA, a few ms)
+    // on the side stream, beside the uploads and the shard selection of the main stream.
     const uint32_t n_in = d.npts;
-    uint32_t* offs_pinned = nullptr;
-    std::thread offs_thread;
+    float2* d_in_own = nullptr;
+    uint32_t *d_offs_own = nullptr, *d_cursor = nullptr;
+    struct Scratch { // scratch allocations go back to the pool on every path out
+        clumpy_cuda_ctx* c; float2*& p; uint32_t*& o; uint32_t*& q;
+        ~Scratch() { cudaStreamSynchronize(c->aux_stream); dev_release(c, p); dev_release(c, o); dev_release(c, q); }
+    } scratch{ctx, d_in_own, d_offs_own, d_cursor};
+    if (n_in && !(d.age_offset && d.age_on_device)) DEV_ALLOC(ctx, &d_offs_own, (size_t)n_in * 4);
     if (!d.age_offset && n_in) {
-        offs_pinned = static_cast<uint32_t*>(ctx_pinned_get(ctx, (size_t)n_in * 4));
-        if (!offs_pinned) return CLUMPY_ERR_NOMEM;
-        const uint32_t nframes = a->nframes;
-        offs_thread = std::thread([=] { age_offsets_host(nframes, n_in, offs_pinned); });
+        CK(cudaEventRecord(a->advected, ctx->stream)); // the allocation is ordered on the main stream
+        CK(cudaStreamWaitEvent(ctx->aux_stream, a->advected, 0));
+        int rc = launch_age_offsets(ctx, ctx->aux_stream, a->nframes, n_in, d_offs_own);
+        if (rc) return rc;
+        CK(cudaEventRecord(a->side_done, ctx->aux_stream));
     }
-    trace_mark(ctx, "advect_begin: events, offsets thread started");
-    struct Joiner { // whatever happens below, the thread is joined and the pinned buffer goes back to the cache
-        std::thread& t; clumpy_cuda_ctx* c; uint32_t* p; size_t bytes;
-        ~Joiner() { if (t.joinable()) t.join(); cudaStreamSynchronize(c->stream); ctx_pinned_put(c, p, bytes); }
-    } joiner{offs_thread, ctx, offs_pinned, (size_t)n_in * 4};
+    trace_mark(ctx, "advect_begin: events, reset offsets enqueued");
 
     // the field: used in place when it is already on the device
     if (d.vel_on_device) {
@@ -394,12 +397,6 @@ static int advect_begin_impl(clumpy_advect* a, const clumpy_advect_desc& d) {
 
     // the caller's points on the device
     const float2* d_in = reinterpret_cast<const float2*>(d.pts);
-    float2* d_in_own = nullptr;
-    uint32_t *d_offs_own = nullptr, *d_cursor = nullptr;
-    struct Scratch { // scratch allocations go back to the pool on every path out
-        clumpy_cuda_ctx* c; float2*& p; uint32_t*& o; uint32_t*& q;
-        ~Scratch() { dev_release(c, p); dev_release(c, o); dev_release(c, q); }
-    } scratch{ctx, d_in_own, d_offs_own, d_cursor};
     if (!d.pts_on_device && n_in) {
         DEV_ALLOC(ctx, &d_in_own, (size_t)n_in * 8);
         CK(cudaMemcpyAsync(d_in_own, d.pts, (size_t)n_in * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -472,14 +469,8 @@ static int advect_begin_impl(clumpy_advect* a, const clumpy_advect_desc& d) {
     // reset offsets on the device
     const uint32_t* d_offs = d.age_offset;
     if (n_in && !(d.age_offset && d.age_on_device)) {
-        const uint32_t* src = d.age_offset;
-        if (!src) {
-            offs_thread.join();
-            src = offs_pinned;
-            trace_mark(ctx, "advect_begin: age offsets (host thread, overlapped with the above)");
-        }
-        DEV_ALLOC(ctx, &d_offs_own, (size_t)n_in * 4);
-        CK(cudaMemcpyAsync(d_offs_own, src, (size_t)n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (d.age_offset) CK(cudaMemcpyAsync(d_offs_own, d.age_offset, (size_t)n_in * 4, cudaMemcpyHostToDevice, ctx->stream));
+        else CK(cudaStreamWaitEvent(ctx->stream, a->side_done, 0)); // drawn on the side stream (above)
         d_offs = d_offs_own;
     }
     if (n) {
@@ -497,7 +488,7 @@ static int advect_begin_impl(clumpy_advect* a, const clumpy_advect_desc& d) {
     rc = sort_points(a, d.regroup);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream)); // host buffers of the caller are free again; errors surface here
-    trace_mark(ctx, "advect_begin: offsets upload, point records, sort");
+    trace_mark(ctx, "advect_begin: reset offsets, point records, sort");
     return CLUMPY_OK;
 }
 

@@ -93,19 +93,12 @@ CLUMPY_API int clumpy_cuda_advect_points_multi(const int* devices, int ndevices,
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cleanup(); set_error("cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e)); return CLUMPY_ERR_CUDA; }
             cudaGetLastError();
         }
-    // reset offsets: drawn once for the whole list (they follow the ORIGINAL point index)
-    std::vector<uint32_t> offs_own;
-    std::thread offs_thread;
-    if (!age_offset && npts) {
-        offs_own.resize(npts);
-        offs_thread = std::thread([&] { age_offsets_host(nframes, npts, offs_own.data()); });
-    }
+    // reset offsets (they follow the ORIGINAL point index): every rank draws the whole list on its own device when
+    // the caller has none (age_offset == NULL goes through to clumpy_cuda_advect_begin_ex)
     // home-row strips of equal point count
     std::vector<uint32_t> rows(height, 0);
     rc = clumpy_cuda_row_histogram(ranks[0].ctx, pts_host, npts, 0, height, rows.data());
-    if (offs_thread.joinable()) offs_thread.join();
     if (rc) { cleanup(); return rc; }
-    if (!age_offset) age_offset = offs_own.data();
     const std::vector<uint32_t> edges = strip_edges(rows, world);
     uint32_t capacity = 1;
     for (int r = 0; r < world; ++r) {

@@ -83,6 +83,8 @@ void ctx_pinned_put(clumpy_cuda_ctx* ctx, void* p, size_t bytes);
 
 // advect_points.cc:127-135 (age_offsets.cc)
 void age_offsets_host(uint32_t nframes, uint32_t npts, uint32_t* dst);
+// the same draws generated on the device (age_offsets_dev.cu), asynchronous on `stream`
+int launch_age_offsets(clumpy_cuda_ctx* ctx, cudaStream_t stream, uint32_t nframes, uint32_t n, uint32_t* out_dev);
 
 // ---- min / max of a float stream, reduced on the device ------------------------------------
 int minmax_reset(clumpy_cuda_ctx* ctx);

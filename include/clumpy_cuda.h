@@ -170,12 +170,15 @@ int clumpy_cuda_splat_multi(const int* devices, int ndevices, const float* pts_h
 /* Host helper: the per-point reset offsets of commands/advect_points.cc:127-135
  * (std::mt19937 seeded with 0 + std::uniform_int_distribution<>(0, nframes-1), libstdc++). */
 int clumpy_cuda_age_offsets(uint32_t nframes, uint32_t npts, uint32_t* out);
+/* The same draws into DEVICE memory, generated on the device (asynchronous on the context's stream): what
+ * clumpy_cuda_advect_begin does when age_offset is NULL. */
+int clumpy_cuda_age_offsets_dev(clumpy_cuda_ctx* ctx, uint32_t nframes, uint32_t npts, uint32_t* out_dev);
 
 /* Set-up of commands/advect_points.cc:83-135: uploads the points (npts, 2) and the velocity
  * field (height, width, 2), allocates the u8 framebuffer (zeroed) and the splat accumulator.
  * `decay` is the non-negative decay; `wrapx` != 0 is what the command derives from a negative
- * decay argument (:78-81).  age_offset may be NULL, in which case clumpy_cuda_age_offsets is
- * used.  nframes is the number of RECORDED frames; the run has 2*nframes simulation frames. */
+ * decay argument (:78-81).  age_offset may be NULL, in which case the offsets of clumpy_cuda_age_offsets
+ * are drawn (on the device).  nframes is the number of RECORDED frames; the run has 2*nframes simulation frames. */
 int clumpy_cuda_advect_begin(clumpy_cuda_ctx* ctx, const float* pts_host, uint32_t npts,
                              const float* vel_host, uint32_t width, uint32_t height,
                              float step_size, int kernel_size, float decay, int wrapx,

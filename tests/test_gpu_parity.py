@@ -645,6 +645,24 @@ def test_age_offset_sentinel_never_resets(ctx, oracle_mod):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("nframes,n", [(1000, 16_777_216), (1, 5000), (2, 70_001), (240, 1_000_003), (65535, 300_000),
+                                        (1_000_003, 200_000), (3 << 29, 150_000), (0x7FFFFFFF, 100_000), (0x80000000, 100_000)])
+def test_age_offsets_drawn_on_the_device_match_the_host(ctx, nframes, n):
+    """advect_points.cc:127-135 on the device (csrc/age_offsets_dev.cu) against the host restatement, which
+    tests/test_abi.py pins to <random> itself.  3 << 29 rejects a quarter of the generator's words (2^32 mod range
+    = 2^30), the other ranges between none and a handful: both the straight and the compacting path run."""
+    import torch
+    import clumpy_b200
+    out = torch.full((n + 7,), -559038737, dtype=torch.int32, device="cuda")  # 0xDEADBEEF: the slack past n must stay untouched
+    torch.cuda.synchronize()
+    ctx.age_offsets_dev(nframes, n, out.data_ptr())
+    ctx.sync()
+    got = out.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got[:n], clumpy_b200.age_offsets(nframes, n))
+    assert (got[n:] == 0xDEADBEEF).all()
+
+
 # ---- parity at the sizes of the BASELINE configs (VERDICT r1: "never parity-checked at their sizes") --------------
 
 @pytest.mark.gpu
