@@ -375,6 +375,7 @@ static int advect_begin_impl(clumpy_advect* a, const clumpy_advect_desc& d) {
         ~Scratch() { cudaStreamSynchronize(c->aux_stream); dev_release(c, p); dev_release(c, o); dev_release(c, q); }
     } scratch{ctx, d_in_own, d_offs_own, d_cursor};
     if (n_in && !(d.age_offset && d.age_on_device)) DEV_ALLOC(ctx, &d_offs_own, (size_t)n_in * 4);
+    trace_mark(ctx, "advect_begin: events, offsets buffer");
     if (!d.age_offset && n_in) {
         CK(cudaEventRecord(a->advected, ctx->stream)); // the allocation is ordered on the main stream
         CK(cudaStreamWaitEvent(ctx->aux_stream, a->advected, 0));

@@ -15,6 +15,11 @@
 // with <random> itself for ranges from 1 to 2^31 - 1.
 #include <algorithm>
 #include <cstdint>
+#include <future>
+#include <mutex>
+#include <vector>
+
+#include "mt_checkpoints.h"
 
 namespace {
 
@@ -50,6 +55,15 @@ struct Mt19937 {
             out[k] = y;
         }
         pos = 0;
+    }
+    // the state alone (no outputs): what the checkpoint table needs
+    __attribute__((target_clones("avx2", "default"))) void advance_state() {
+        uint32_t* __restrict__ p = state;
+#pragma GCC ivdep
+        for (int k = 0; k < 227; ++k) p[k] = twist(p[k], p[k + 1], p[k + 397]);
+#pragma GCC ivdep
+        for (int k = 227; k < 623; ++k) p[k] = twist(p[k], p[k + 1], p[k - 227]);
+        p[623] = twist(p[623], p[0], p[396]);
     }
     inline uint32_t next() {
         if (pos == 624) refill();
@@ -90,6 +104,37 @@ void age_offsets_host(uint32_t nframes, uint32_t npts, uint32_t* dst) {
         }
         i += done;
     }
+}
+
+// ---- generator states at fixed distances, for the device-side draws (age_offsets_dev.cu) --------------------------
+// The reference always seeds with 0 (advect_points.cc:129), so the generator's word sequence is one fixed sequence
+// and its state after MT_CKPT_BLOCKS * s refills is a constant.  The table of those states lets MT_CKPT_COUNT CTAs
+// generate disjoint stretches of the sequence at once.  It is computed once per process on a background thread
+// (started when the first context is created; ~10 ms of one core) instead of being shipped as 160 KB of literals.
+namespace {
+std::once_flag ckpt_once;
+std::shared_future<std::vector<uint32_t>> ckpt_future;
+
+std::vector<uint32_t> compute_checkpoints() {
+    std::vector<uint32_t> table((size_t)MT_CKPT_COUNT * 624);
+    Mt19937 g;
+    g.seed(0);
+    for (int s = 0; s < MT_CKPT_COUNT; ++s) {
+        std::copy(g.state, g.state + 624, table.begin() + (size_t)s * 624);
+        if (s + 1 < MT_CKPT_COUNT)
+            for (int b = 0; b < MT_CKPT_BLOCKS; ++b) g.advance_state();
+    }
+    return table;
+}
+} // namespace
+
+void mt_checkpoints_prefetch() {
+    std::call_once(ckpt_once, [] { ckpt_future = std::async(std::launch::async, compute_checkpoints).share(); });
+}
+
+const uint32_t* mt_checkpoints() {
+    mt_checkpoints_prefetch();
+    return ckpt_future.get().data();
 }
 
 } // namespace clumpy

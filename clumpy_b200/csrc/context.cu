@@ -1,5 +1,6 @@
 // context.cu -- context lifecycle, memory helpers, timers and error reporting of the C ABI.
 #include "internal.h"
+#include "mt_checkpoints.h"
 
 #include <cstring>
 
@@ -121,6 +122,7 @@ CLUMPY_API int clumpy_cuda_create(int device, void* stream, clumpy_cuda_ctx** ou
 
 static int create_impl(clumpy_cuda_ctx* ctx, int device, void* stream, const cudaDeviceProp& prop) {
     ctx->device = device;
+    mt_checkpoints_prefetch(); // (background thread, once per process: the reset-offset generator's table)
     ctx->sm_count = prop.multiProcessorCount;
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
     if (stream) {
@@ -161,6 +163,7 @@ CLUMPY_API void clumpy_cuda_destroy(clumpy_cuda_ctx* ctx) {
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->d_minmax) cudaFree(ctx->d_minmax);
+    if (ctx->mt_checkpoints_dev) cudaFree(ctx->mt_checkpoints_dev);
     if (ctx->h_minmax) cudaFreeHost(ctx->h_minmax);
     cudaGetLastError();
     for (auto& b : ctx->pinned_cache) cudaFreeHost(b.first);

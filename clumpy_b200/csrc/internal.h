@@ -59,6 +59,7 @@ struct clumpy_cuda_ctx {
     size_t l2_bytes = 0;
     cudaStream_t stream = nullptr;      // compute stream (caller's or ours)
     bool own_stream = false;
+    uint32_t* mt_checkpoints_dev = nullptr; // mt19937 states + per-stretch scratch of the reset-offset generator (age_offsets_dev.cu)
     cudaStream_t copy_stream = nullptr; // frame D2H side stream
     cudaStream_t aux_stream = nullptr;  // high-priority side stream: the receiving half of a multi-GPU group (drain +
                                         // band composite), and the composite work of a single-GPU group when asked

@@ -647,11 +647,14 @@ def test_age_offset_sentinel_never_resets(ctx, oracle_mod):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("nframes,n", [(1000, 16_777_216), (1, 5000), (2, 70_001), (240, 1_000_003), (65535, 300_000),
-                                        (1_000_003, 200_000), (3 << 29, 150_000), (0x7FFFFFFF, 100_000), (0x80000000, 100_000)])
+                                        (1_000_003, 200_000), (3 << 29, 150_000), (3 << 29, 2_000_000), (0x7FFFFFFF, 100_000),
+                                        (0x80000000, 100_000), (7, 34_500_000), (524_160, 524_160), (1000, 524_161)])
 def test_age_offsets_drawn_on_the_device_match_the_host(ctx, nframes, n):
     """advect_points.cc:127-135 on the device (csrc/age_offsets_dev.cu) against the host restatement, which
     tests/test_abi.py pins to <random> itself.  3 << 29 rejects a quarter of the generator's words (2^32 mod range
-    = 2^30), the other ranges between none and a handful: both the straight and the compacting path run."""
+    = 2^30), the other ranges between none and a handful: both the straight and the compacting path run.  The
+    generator runs as up to 64 stretches from a table of states (16.7 M draws: 33 of them; 34.5 M: all 64 and the
+    open-ended tail; 524 160 is exactly one stretch)."""
     import torch
     import clumpy_b200
     out = torch.full((n + 7,), -559038737, dtype=torch.int32, device="cuda")  # 0xDEADBEEF: the slack past n must stay untouched

@@ -1,0 +1,8 @@
+import sys, os
+sys.path.insert(0, os.getcwd())
+import torch, clumpy_b200
+ctx = clumpy_b200.Context(0)
+out = torch.zeros(16_777_216 + 8, dtype=torch.int32, device="cuda")
+for n in (16_777_216, 2_097_152):
+    for rep in range(3):
+        ctx.timer_start(); ctx.age_offsets_dev(1000, n, out.data_ptr()); print("age_offsets_dev", n, "draws:", round(ctx.timer_stop(), 3), "ms")
