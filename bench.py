@@ -378,7 +378,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "seconds": dt,
                 "what": "clumpy_cuda_advect_points with pinned host buffers: H2D of points + field, reset offsets drawn "
-                        f"on a host thread and uploaded, sort, {e2e_steps} simulation frames, D2H of {nrec} recorded frames; "
+                        f"on the device, sort, {e2e_steps} simulation frames, D2H of {nrec} recorded frames; "
                         "after one untimed call of the same command (2 recorded frames)"},
         "gpu_launches": int(launches),
         "roofline": roof,
@@ -496,14 +496,21 @@ def run_multi(args):
                 torch.cuda.synchronize()
                 note(f"e2e +{(time.perf_counter() - t_e2e) * 1e3:8.2f} ms  {what}")
 
-        d_pts = pts.to(device, non_blocking=True)                   # H2D: all points (the shard is selected on the device)
-        d_band = vel_band.to(device, non_blocking=True)             # H2D: this rank's rows of the field
+        # H2D: this rank's 1/world of the point list and its rows of the field; both are then all-gathered over NVLink
+        # (every rank needs the whole list to select its strip, and the whole field)
+        if n % world == 0:
+            d_slice = pts[rank * (n // world):(rank + 1) * (n // world)].to(device, non_blocking=True)
+            d_pts = torch.empty((n, 2), dtype=torch.float32, device=device)
+            dist.all_gather_into_tensor(d_pts, d_slice)
+        else:
+            d_pts = pts.to(device, non_blocking=True)
+        d_band = vel_band.to(device, non_blocking=True)
         field = torch.empty((world, vel_band.shape[0], w, 2), dtype=torch.float32, device=device)
         dist.all_gather_into_tensor(field, d_band)                  # NVLink: every rank gets the whole field
         field = field.reshape(-1, w, 2) if h % world == 0 else torch.cat(
             [field[r, :mg.field_rows(h, world, r)[1] - mg.field_rows(h, world, r)[0]] for r in range(world)])
         lap("points + field band uploaded, field all-gathered")
-        r2 = make_run(d_pts, field, nr)                              # offsets on a host thread, shard select, sort, IPC handles
+        r2 = make_run(d_pts, field, nr)                              # reset offsets, shard select, sort, IPC handles
         lap("sharded run set up")
         r2.step(nr)                                                  # warm-up half
         r2.record(nr, host_frames, host_frames.shape[1] * w)         # recorded half: D2H of the band of every frame
@@ -546,10 +553,10 @@ def run_multi(args):
                              "phases, its part of the field, 16 band buffers and the image band -- more than the 126 MB of L2 at every N"},
             "clocks": clocks,
             "e2e": {"value": n * e2e_steps / dt, "unit": UNIT,
-                    "h2d_bytes_per_step": (world * n * 8 + w * h * 8) / e2e_steps, "d2h_bytes_per_step": nrec * w * h / e2e_steps,
+                    "h2d_bytes_per_step": ((1 if n % world == 0 else world) * n * 8 + w * h * 8) / e2e_steps, "d2h_bytes_per_step": nrec * w * h / e2e_steps,
                     "steps": e2e_steps, "seconds": dt,
-                    "what": "per rank, from pinned host buffers: H2D of all points + its rows of the field, field all-gather over NVLink, "
-                            "row histogram + shard selection on the device, reset offsets drawn on a host thread and uploaded, sort, inbox "
+                    "what": "per rank, from pinned host buffers: H2D of its 1/N of the point list + its rows of the field, both all-gathered "
+                            "over NVLink, row histogram + shard selection on the device, reset offsets drawn on the device, sort, inbox "
                             "set-up + IPC handle exchange, frames, D2H of its row band of every recorded frame; after one untimed call of the same"},
             "gpu_launches": int(launches),
             "roofline": roof,
