@@ -385,24 +385,28 @@ static int advect_begin_impl(clumpy_advect* a, const clumpy_advect_desc& d) {
     }
     trace_mark(ctx, "advect_begin: events, reset offsets enqueued");
 
-    // the field: used in place when it is already on the device
-    if (d.vel_on_device) {
-        a->vel = const_cast<float2*>(reinterpret_cast<const float2*>(d.vel));
-        a->vel_owned = false;
-    } else {
-        DEV_ALLOC(ctx, &a->vel, npix * 8);
-        trace_mark(ctx, "advect_begin: field allocated");
-        CK(cudaMemcpyAsync(a->vel, d.vel, npix * 8, cudaMemcpyHostToDevice, ctx->stream));
-        trace_mark(ctx, "advect_begin: field upload");
-    }
-
-    // the caller's points on the device
+    // the caller's points on the device.  They go up BEFORE the field: the set-up kernels that need them (shard
+    // selection, point records, sort) then run beside the field's upload, which has a stream of its own.
     const float2* d_in = reinterpret_cast<const float2*>(d.pts);
     if (!d.pts_on_device && n_in) {
         DEV_ALLOC(ctx, &d_in_own, (size_t)n_in * 8);
         CK(cudaMemcpyAsync(d_in_own, d.pts, (size_t)n_in * 8, cudaMemcpyHostToDevice, ctx->stream));
         d_in = d_in_own;
         trace_mark(ctx, "advect_begin: point upload");
+    }
+    // the field: used in place when it is already on the device
+    bool field_in_flight = false;
+    if (d.vel_on_device) {
+        a->vel = const_cast<float2*>(reinterpret_cast<const float2*>(d.vel));
+        a->vel_owned = false;
+    } else {
+        DEV_ALLOC(ctx, &a->vel, npix * 8);
+        CK(cudaEventRecord(a->frame_ready, ctx->stream)); // (allocation and the points' copy are ordered on the main stream)
+        CK(cudaStreamWaitEvent(ctx->copy_stream, a->frame_ready, 0));
+        CK(cudaMemcpyAsync(a->vel, d.vel, npix * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(a->frames_ready, ctx->copy_stream));
+        field_in_flight = true;
+        trace_mark(ctx, "advect_begin: field upload");
     }
     // which of them this run simulates
     const bool shard = d.shard_row_hi > d.shard_row_lo;
@@ -488,6 +492,7 @@ static int advect_begin_impl(clumpy_advect* a, const clumpy_advect_desc& d) {
     }
     rc = sort_points(a, d.regroup);
     if (rc) return rc;
+    if (field_in_flight) CK(cudaStreamWaitEvent(ctx->stream, a->frames_ready, 0));
     CK(cudaStreamSynchronize(ctx->stream)); // host buffers of the caller are free again; errors surface here
     trace_mark(ctx, "advect_begin: reset offsets, point records, sort");
     return CLUMPY_OK;
