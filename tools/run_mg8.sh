@@ -1,10 +1,16 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tools/check_multigpu.py > gpurun_out/check_mg8.log 2>&1; tail -9 gpurun_out/check_mg8.log | cut -c1-150
-for K in 20 2000; do
-  CLUMPY_BENCH_VERBOSE=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps $K --warmup 5 > gpurun_out/bench_mg8_$K.json 2> gpurun_out/bench_mg8_$K.err
+#!/bin/bash
+# The multi-GPU lines on an 8-GPU box (through gpurun --gpus 8): parity over NVLink at 8 ranks, then bench.py at
+# N = 4 (20 steps) and N = 8 (20 and 2000 steps), results under gpurun_out/.
+run() { # N K port
+  CLUMPY_BENCH_VERBOSE=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $3 bench.py --gpus $1 --steps $2 --warmup 5 > gpurun_out/bench_mg$1_$2.json 2> gpurun_out/bench_mg$1_$2.err
   python -c "
-import json; d=json.load(open('gpurun_out/bench_mg8_$K.json')); k=d['roofline']['per_rank_kernel_ms']
-print('K=$K ms/step', d['ms_per_step'], 'steady', d['steady_ms_per_step'], 'e2e', d['e2e']['seconds'])
+import json; d=json.load(open('gpurun_out/bench_mg$1_$2.json')); k=d['roofline']['per_rank_kernel_ms']
+print('N=$1 K=$2 ms/step', round(d['ms_per_step'],5), 'steady', round(d['steady_ms_per_step'],5), 'e2e', round(d['e2e']['seconds'],4))
 print(' route', [round(x,4) for x in k['route_per_frame']]); print(' drain', [round(x,4) for x in k['drain_incl_wait_per_frame']]); print(' comp ', [round(x,4) for x in k['composite_per_frame']])
-" || tail -5 gpurun_out/bench_mg8_$K.err
-done
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --workload c3 --steps 20 --warmup 5 > gpurun_out/bench_c3_mg8.json 2> gpurun_out/bench_c3_mg8.err; cat gpurun_out/bench_c3_mg8.json | cut -c1-900; tail -3 gpurun_out/bench_c3_mg8.err
+" || tail -5 gpurun_out/bench_mg$1_$2.err
+}
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tools/check_multigpu.py > gpurun_out/check_mg8.log 2>&1; tail -9 gpurun_out/check_mg8.log | cut -c1-150
+run 4 20 29512
+run 8 20 29513
+run 8 2000 29514
+grep "bench rank 0" gpurun_out/bench_mg8_20.err | grep "e2e +" | tail -5
