@@ -128,7 +128,6 @@ struct clumpy_advect {
         bool on = false;
         int rank = 0, world = 1, chunk = 0;
         int fuse = ROUTE_MAX_FUSE;   // frames per route launch
-        int minb = 6;                // route kernel variant: 6 CTAs per SM (40 registers) or 8 (32)
         uint32_t nregion = 0;        // regions of ROUTE_REGION entry slots per source segment
         bool inbox_owned = true;     // false: the caller's arena (kept across runs together with the peers' mappings of it)
         uint32_t* inbox = nullptr;   // [ROUTE_PARITIES][ROUTE_MAX_FUSE][world][nregion * ROUTE_REGION] cell indices, then
@@ -579,16 +578,12 @@ CLUMPY_API int clumpy_cuda_row_histogram(clumpy_cuda_ctx* ctx, const float* pts,
 template <bool WRAP, int MODE, typename OffT>
 static void launch_advect_t(clumpy_advect* a, uint32_t phase, int nf, const HistRing& ring) {
     const uint32_t grid = ceil_div(a->npts, ADVECT_THREADS * ADVECT_PTS);
-    const int hints = env_int("CLUMPY_CUDA_HINTS", 0), minb = env_int("CLUMPY_CUDA_ADVECT_MINB", 1); // (A/B switches)
+    const int hints = env_int("CLUMPY_CUDA_HINTS", 0); // (A/B switch)
     const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch, a->keep_pos ? 1 : 0, hints};
-    if (minb == 8)
-        advect_fused_kernel<WRAP, MODE, OffT, 8><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
-            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase,
-            a->nframes, nf, g, ring);
-    else
-        advect_fused_kernel<WRAP, MODE, OffT, 6><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>( // 6 CTAs per SM: 40 registers
-            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase,
-            a->nframes, nf, g, ring);
+    // (6 CTAs of 40 registers per SM; 8 of 32 was measured and lost: profiles/r2_sweep_single_b.jsonl)
+    advect_fused_kernel<WRAP, MODE, OffT><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
+        a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, phase,
+        a->nframes, nf, g, ring);
 }
 
 template <bool WRAP, int MODE>
@@ -975,15 +970,10 @@ template <bool WRAP, bool SPLAT, bool F16, typename OffT>
 static void launch_route_t(clumpy_advect* a, const RouteDev& rd) {
     const uint32_t grid = ceil_div(a->npts, ROUTE_BLOCK); // CTA c owns region c of its segments
     const GeomDev g{a->geom.width, a->geom.height, a->geom.halo, a->geom.pitch, a->keep_pos ? 1 : 0, 0};
-    // CLUMPY_ROUTE_SMEM_KB=<n> (A/B): n KB of unused dynamic shared memory per CTA, to cap how many CTAs of this
-    // kernel an SM holds (227 KB / n) and leave room for the drain / composite launches of the side stream
-    const size_t pad = (size_t)std::min(std::max(env_int("CLUMPY_ROUTE_SMEM_KB", 0), 0), 48) * 1024;
-    if (a->route.minb == 8)
-        advect_route_kernel<WRAP, SPLAT, F16, OffT, 8><<<grid, ADVECT_THREADS, pad, a->ctx->stream>>>(
-            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);
-    else
-        advect_route_kernel<WRAP, SPLAT, F16, OffT, 6><<<grid, ADVECT_THREADS, pad, a->ctx->stream>>>(
-            a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);
+    // (6 CTAs of 40 registers per SM.  Measured and dropped: 8 CTAs of 32 registers -- spills, 0.0133 against 0.0125 ms per
+    // frame -- and capping the CTAs per SM with unused shared memory to leave room for the side stream's launches.)
+    advect_route_kernel<WRAP, SPLAT, F16, OffT><<<grid, ADVECT_THREADS, 0, a->ctx->stream>>>(
+        a->pos, a->orig, (const OffT*)a->offset, a->npts, a->vel, a->width, a->height, a->step_size, g, rd);
 }
 
 static size_t route_inbox_layout(uint32_t capacity, int world, uint32_t* nregion, size_t* entries_per_frame, size_t* cnt_per_frame,
@@ -1028,7 +1018,6 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     REQUIRE(world == 1 || rt.chunk >= 2 * adv->geom.halo, "bands thinner than the sprite are not supported");
     if (adv->overlap_opt < 0) adv->overlap = true; // the receiving half waits for other GPUs: keep it off the main stream
     rt.fuse = std::min(std::max(env_int("CLUMPY_ROUTE_FUSE", adv->cell_mode == CELL_F16 ? ROUTE_MAX_FUSE : 4), 1), ROUTE_MAX_FUSE);
-    rt.minb = env_int("CLUMPY_ROUTE_MINB", 6) == 8 ? 8 : 6;
     rt.timeout_ns = (unsigned long long)std::max(1, env_int("CLUMPY_ROUTE_TIMEOUT_MS", 2000)) * 1000000ull;
     // the regroup period is part of the protocol (every rank cuts its groups at the same frames): whole groups
     if (adv->regroup_every) adv->regroup_every = std::max<uint32_t>((uint32_t)rt.fuse, adv->regroup_every / (uint32_t)rt.fuse * (uint32_t)rt.fuse);
@@ -1063,10 +1052,8 @@ CLUMPY_API int clumpy_cuda_advect_route_begin(clumpy_advect* adv, int rank, int 
     // the (zero) framebuffer as it is; the route kernels are loaded without being run.
     {
         cudaFuncAttributes fa;
-#define ROUTE_LOAD2(W, S, F) CK(adv->off16 ? (rt.minb == 8 ? cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, F, uint16_t, 8>) \
-                                                           : cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, F, uint16_t, 6>)) \
-                                          : (rt.minb == 8 ? cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, F, uint32_t, 8>) \
-                                                           : cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, F, uint32_t, 6>)))
+#define ROUTE_LOAD2(W, S, F) CK(adv->off16 ? cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, F, uint16_t>) \
+                                          : cudaFuncGetAttributes(&fa, advect_route_kernel<W, S, F, uint32_t>))
 #define ROUTE_LOAD(W, S) do { if (adv->cell_mode == CELL_F16) ROUTE_LOAD2(W, S, true); else ROUTE_LOAD2(W, S, false); } while (0)
         if (adv->wrapx) { ROUTE_LOAD(true, true); ROUTE_LOAD(true, false); }
         else            { ROUTE_LOAD(false, true); ROUTE_LOAD(false, false); }

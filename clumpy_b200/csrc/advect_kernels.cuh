@@ -99,8 +99,8 @@ struct HistRing { // frame f of the group counts into image (first + f) % count
     __host__ __device__ uint32_t* image(int f) const { return base + (size_t)((first + f) % count) * stride_words; }
 };
 
-template <bool WRAP, int MODE, typename OffT, int MINB>
-__global__ void __launch_bounds__(ADVECT_THREADS, MINB)
+template <bool WRAP, int MODE, typename OffT>
+__global__ void __launch_bounds__(ADVECT_THREADS, 6)
 advect_fused_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                     const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
                     uint32_t width, uint32_t height, float step, uint32_t phase0, uint32_t nframes, int nf,
@@ -365,8 +365,8 @@ __device__ __forceinline__ void route_group_fence(const RouteDev& rt, bool cta_s
     }
 }
 
-template <bool WRAP, bool SPLAT, bool F16, typename OffT, int MINB>
-__global__ void __launch_bounds__(ADVECT_THREADS, MINB)
+template <bool WRAP, bool SPLAT, bool F16, typename OffT>
+__global__ void __launch_bounds__(ADVECT_THREADS, 6)
 advect_route_kernel(float2* __restrict__ pos, const float2* __restrict__ orig,
                     const OffT* __restrict__ offset, uint32_t npts, const float2* __restrict__ vel,
                     uint32_t width, uint32_t height, float step, GeomDev g, RouteDev rt) {

@@ -32,10 +32,11 @@ def main():
     torch.cuda.synchronize()
     d_pts = torch.from_numpy(synth_points(n, w, h)).cuda()
     d_off = torch.from_numpy(clumpy_b200.age_offsets(cfg["nframes"], n).astype("int32")).cuda()
-    base = dict(fuse=8, overlap=-1, threads="512", tile="3,2", hints="0", minb="1", regroup=0)
-    variants = [{}] + [dict(hints=str(hb)) for hb in (1, 2, 3, 4, 8, 12, 5, 15)] + [dict(minb="8"), dict(tile="4,1"), dict(regroup=96), dict(regroup=128),
-                dict(tile="4,1", minb="8"), dict(tile="4,1", minb="8", hints="1"), dict(tile="4,1", minb="8", hints="13"), dict(fuse=6, tile="4,1", minb="8"),
-                dict(overlap=1, tile="4,1", minb="8")]
+    # (round 2's sweep b also had an "8 CTAs of 32 registers per SM" variant of the advect kernel -- the advect_minb
+    # column of profiles/r2_sweep_single_b.jsonl; it lost and the switch is gone)
+    base = dict(fuse=8, overlap=-1, threads="512", tile="4,1", hints="0", regroup=0)
+    variants = [{}] + [dict(hints=str(hb)) for hb in (1, 2, 3, 4, 8, 12, 5, 15)] + [dict(tile="3,2"), dict(regroup=96), dict(regroup=128),
+                dict(fuse=6), dict(overlap=1)]
     if quick:
         variants = variants[:3]
     for var in variants:
@@ -45,7 +46,6 @@ def main():
         os.environ["CLUMPY_CUDA_SORT_TILE"] = tile
         # (the library reads these two once per process: they are fixed per run of this script unless re-exec'd)
         os.environ["CLUMPY_CUDA_HINTS"] = c["hints"]
-        os.environ["CLUMPY_CUDA_ADVECT_MINB"] = c["minb"]
         adv = ctx.advect(d_pts.data_ptr(), d_vel.data_ptr(), cfg["step_size"], cfg["kernel_size"], cfg["decay"], cfg["nframes"],
                          age_offset=d_off.data_ptr(), npts=n, width=w, height=h, fuse=fuse, overlap=overlap, regroup=c["regroup"])
         adv.step(1200)
@@ -60,7 +60,7 @@ def main():
         a_alone, c_alone, _ = adv.profile_stages(16, serial=True)
         adv.close()
         print(json.dumps({"fuse": fuse, "overlap": overlap, "composite_threads": int(thr), "sort_tile_log2": tile, "hints": c["hints"],
-                          "advect_minb": c["minb"], "regroup": c["regroup"], "ms_per_step": ms,
+                          "regroup": c["regroup"], "ms_per_step": ms,
                           "advect_ms_per_frame_live": a_live / nf, "composite_ms_per_frame_live": c_live / nf,
                           "advect_ms_per_frame_alone": a_alone / nf, "composite_ms_per_frame_alone": c_alone / nf}), flush=True)
     ctx.close()
