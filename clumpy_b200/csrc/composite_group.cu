@@ -136,10 +136,30 @@ __device__ __forceinline__ uint32_t lookup4(const uint8_t* __restrict__ tab, uin
 
 struct CellRow { uint32_t w0, w1, e; }; // cells (x0-1, x0), (x0+1, x0+2), (x0+3, x0+4) as half2 bit patterns
 
+// The GC_ROWS + 2 counter rows a lane needs for frame f of its tile, as they are in memory (no shuffles here: the loads
+// stay in flight until the words are used).
+template <int N>
+__device__ __forceinline__ void load_rows(const GroupCompositeArgs& a, int f, int y0, int tx, int lane, uint64_t pol, CellRow (&dst)[N]) {
+    const __half* base = static_cast<const __half*>(a.cells[f]) + (size_t)y0 * a.pitch + tx * GC_TILE_W + 4 * lane;
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+        const __half* p = base + (size_t)r * a.pitch;
+        const uint2 v = ld_stream_u2(reinterpret_cast<const uint2*>(p), pol);
+        dst[r].w0 = v.x;
+        dst[r].w1 = v.y;
+        dst[r].e = 0u;
+        if (lane == 31) dst[r].e = ld_stream_u1(reinterpret_cast<const uint32_t*>(p + 4), pol);
+    }
+}
+
 // THREADS: 512 by default (64 registers each: half the register file stays free for the advect kernel that
 // shares the SM); 256 (128 registers, no spills) and 1024 exist for A/B runs (CLUMPY_CUDA_COMPOSITE_THREADS).
-template <int K, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2)
+// PREFETCH (K = 3): the counter rows of frame f + 1 are loaded before frame f is worked through -- 30 more registers per
+// thread, which the table's 213 KB make free (one CTA per SM either way).  Without it a warp issues its 10 row
+// loads, waits a DRAM latency, computes, and only then asks for the next frame: 4 warps per scheduler cannot
+// cover that and the issue slots were 45 % busy (round 2 ncu).
+template <int K, int THREADS, bool PREFETCH>
+__global__ void __launch_bounds__(THREADS, (THREADS == 1024 || PREFETCH) ? 1 : 2)
 composite_group_kernel(GroupCompositeArgs a, const uint8_t* __restrict__ table_g, uint32_t table_bytes) {
     extern __shared__ __align__(128) uint8_t tab[];
     __shared__ __align__(8) unsigned long long bar;
@@ -161,24 +181,23 @@ composite_group_kernel(GroupCompositeArgs a, const uint8_t* __restrict__ table_g
         }
     }
 
-    // 2. meanwhile: zero the counter images of the group before this one (they were read by the launch
-    //    before this one on the same stream and are counted into again two groups on)
+    // 2. (the counter images of the group before this one -- read by the launch before this one on the same stream,
+    //    counted into again two groups on -- are zeroed slice by slice inside the tile loop below, where the stores
+    //    share the DRAM with the latency-bound reads of the composite; as a phase of its own in front of it the
+    //    zeroing of 8 x 67 MB was 90 us of the launch's 315)
     const uint64_t zero_pol = (a.hints & 8) ? make_stream_policy() : make_normal_policy();
     const uint64_t cell_pol = (a.hints & 4) ? make_stream_policy() : make_normal_policy();
-    for (int z = 0; z < a.nzero; ++z) {
-        uint4* p = a.zero[z];
-        const uint32_t n16 = a.zero_n16[z];
-        for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < n16; i += gridDim.x * THREADS)
-            st_hint_u4(p + i, make_uint4(0u, 0u, 0u, 0u), zero_pol);
-    }
-
-    // 3. wait for the table
-    {
+    // 3. the wait for the table sits in front of the first lookup (and in front of every way out of the kernel: a CTA
+    //    must not leave while a bulk copy into its shared memory is in flight)
+    bool table_here = false;
+    auto wait_for_table = [&]() {
+        if (table_here) return;
         uint32_t done = 0;
         while (!done)
             asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                          : "=r"(done) : "r"(smem_addr(&bar)) : "memory");
-    }
+        table_here = true;
+    };
 
     // 4. multi-GPU: every source's entries of this group must have arrived (epoch flags in this rank's
     //    memory, stored by the peers' route kernels after a system-scope fence).  Bounded wait.
@@ -197,7 +216,7 @@ composite_group_kernel(GroupCompositeArgs a, const uint8_t* __restrict__ table_g
             fence_ok = ok;
         }
         __syncthreads(); // orders every thread's reads of the cells behind thread 0's acquire
-        if (!fence_ok) return; // the host turns the error count into a failed call (advect.cu)
+        if (!fence_ok) { wait_for_table(); return; } // the host turns the error count into a failed call (advect.cu)
     }
 
     const __half2 lim0 = __float2half2_rn(a.depth[0]), lim1 = __float2half2_rn(a.depth[1]), lim2 = __float2half2_rn(a.depth[2]);
@@ -224,7 +243,15 @@ composite_group_kernel(GroupCompositeArgs a, const uint8_t* __restrict__ table_g
             }
         }
 
+        // this tile's slice of every image to zero: units [zlo, zhi) of zero_units 16-byte units
+        const uint32_t zlo = (uint32_t)((unsigned long long)a.zero_units * (uint32_t)t / (uint32_t)a.ntiles);
+        const uint32_t zhi = (uint32_t)((unsigned long long)a.zero_units * ((uint32_t)t + 1u) / (uint32_t)a.ntiles);
+        CellRow ahead[(K == 3 && PREFETCH) ? GC_ROWS + 2 : 1]; // raw words of the NEXT frame's rows (e: lane 31 only)
+        if (K == 3 && PREFETCH) load_rows(a, 0, y0, tx, lane, cell_pol, ahead);
+        wait_for_table();
         for (int f = 0; f < a.nf; ++f) {
+            for (int z = f; z < a.nzero; z += a.nf) // (a shorter group after a longer one: several images per frame)
+                for (uint32_t i = zlo + (uint32_t)lane; i < zhi; i += 32u) st_hint_u4(a.zero[z] + i, make_uint4(0u, 0u, 0u, 0u), zero_pol);
             // first cell of this lane in padded row (y0 + r): image x = x0 - K / 2, image y = y0 + r - K / 2
             const __half* base = static_cast<const __half*>(a.cells[f]) + (size_t)y0 * a.pitch + tx * GC_TILE_W + 4 * lane;
             if (K == 1) {
@@ -237,17 +264,29 @@ composite_group_kernel(GroupCompositeArgs a, const uint8_t* __restrict__ table_g
                 }
             } else {
                 CellRow row[GC_ROWS + 2];
+                if (PREFETCH) {
 #pragma unroll
-                for (int r = 0; r < GC_ROWS + 2; ++r) {
-                    const __half* p = base + (size_t)r * a.pitch;
-                    const uint2 v = ld_stream_u2(reinterpret_cast<const uint2*>(p), cell_pol);
-                    row[r].w0 = v.x;
-                    row[r].w1 = v.y;
-                    // the next lane's first word = cells (x0+3, x0+4); lane 31 reads it from memory
-                    uint32_t e = 0u;
-                    if (lane == 31) e = ld_stream_u1(reinterpret_cast<const uint32_t*>(p + 4), cell_pol);
-                    const uint32_t up = __shfl_down_sync(0xFFFFFFFFu, v.x, 1);
-                    row[r].e = lane == 31 ? e : up;
+                    for (int r = 0; r < GC_ROWS + 2; ++r) {
+                        row[r].w0 = ahead[r].w0;
+                        row[r].w1 = ahead[r].w1;
+                        // the next lane's first word = cells (x0+3, x0+4); lane 31 has read it from memory
+                        const uint32_t up = __shfl_down_sync(0xFFFFFFFFu, ahead[r].w0, 1);
+                        row[r].e = lane == 31 ? ahead[r].e : up;
+                    }
+                    if (f + 1 < a.nf) load_rows(a, f + 1, y0, tx, lane, cell_pol, ahead);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < GC_ROWS + 2; ++r) {
+                        const __half* p = base + (size_t)r * a.pitch;
+                        const uint2 v = ld_stream_u2(reinterpret_cast<const uint2*>(p), cell_pol);
+                        row[r].w0 = v.x;
+                        row[r].w1 = v.y;
+                        // the next lane's first word = cells (x0+3, x0+4); lane 31 reads it from memory
+                        uint32_t e = 0u;
+                        if (lane == 31) e = ld_stream_u1(reinterpret_cast<const uint32_t*>(p + 4), cell_pol);
+                        const uint32_t up = __shfl_down_sync(0xFFFFFFFFu, v.x, 1);
+                        row[r].e = lane == 31 ? e : up;
+                    }
                 }
 #pragma unroll
                 for (int r = 0; r < GC_ROWS; ++r) {
@@ -283,6 +322,7 @@ composite_group_kernel(GroupCompositeArgs a, const uint8_t* __restrict__ table_g
             }
         }
     }
+    wait_for_table();
 }
 
 int launch_composite_group(clumpy_cuda_ctx* ctx, cudaStream_t stream, const GroupTable& t, GroupCompositeArgs& a) {
@@ -291,6 +331,9 @@ int launch_composite_group(clumpy_cuda_ctx* ctx, cudaStream_t stream, const Grou
     a.tiles_x = (int)ceil_div((uint32_t)a.width, GC_TILE_W);
     a.ntiles = a.tiles_x * (int)ceil_div((uint32_t)a.height, GC_ROWS);
     for (int r = 0; r < 3; ++r) a.depth[r] = (float)t.depth[r];
+    // the kernel zeroes the same slice of every image per tile: the images must have one size (they do: one set)
+    a.zero_units = a.nzero > 0 ? a.zero_n16[0] : 0u;
+    for (int z = 1; z < a.nzero; ++z) REQUIRE(a.zero_n16[z] == a.zero_units, "counter images of one set differ in size");
     bool vec = a.img_pitch % 4 == 0 && (uintptr_t)a.img_in % 4 == 0;
     for (int f = 0; f < a.nf; ++f) vec = vec && (uintptr_t)a.frame_out[f] % 4 == 0;
     a.vec_ok = vec ? 1 : 0;
@@ -301,8 +344,12 @@ int launch_composite_group(clumpy_cuda_ctx* ctx, cudaStream_t stream, const Grou
     int grid = std::min(ctx->sm_count, (int)ceil_div((uint32_t)a.ntiles, (uint32_t)threads / 32));
     if (a.nzero > 0) grid = ctx->sm_count;
     using Kern = void (*)(GroupCompositeArgs, const uint8_t*, uint32_t);
-    const Kern kern = t.kernel_size == 1 ? (threads == 256 ? composite_group_kernel<1, 256> : threads == 1024 ? composite_group_kernel<1, 1024> : composite_group_kernel<1, 512>)
-                                         : (threads == 256 ? composite_group_kernel<3, 256> : threads == 1024 ? composite_group_kernel<3, 1024> : composite_group_kernel<3, 512>);
+    // CLUMPY_CUDA_COMPOSITE_PREFETCH=0|1 (A/B); 1024 threads leave 64 registers each: no room to look ahead
+    const int prefetch_env = [] { const char* v = getenv("CLUMPY_CUDA_COMPOSITE_PREFETCH"); return v ? atoi(v) : 1; }();
+    const bool prefetch = prefetch_env != 0 && t.kernel_size == 3 && threads == 512;
+    const Kern kern = t.kernel_size == 1 ? (threads == 256 ? composite_group_kernel<1, 256, false> : threads == 1024 ? composite_group_kernel<1, 1024, false> : composite_group_kernel<1, 512, false>)
+                    : prefetch           ? composite_group_kernel<3, 512, true>
+                                         : (threads == 256 ? composite_group_kernel<3, 256, false> : threads == 1024 ? composite_group_kernel<3, 1024, false> : composite_group_kernel<3, 512, false>);
     // the opt-in to more than 48 KB of dynamic shared memory is per device and function
     static thread_local std::vector<std::pair<int, Kern>> opted;
     if (std::find(opted.begin(), opted.end(), std::make_pair(ctx->device, kern)) == opted.end()) {

@@ -163,6 +163,7 @@ struct GroupCompositeArgs {
     unsigned long long timeout_ns = 0;
     // filled in by the launcher
     int tiles_x = 0, ntiles = 0, vec_ok = 0;
+    uint32_t zero_units = 0;     // 16-byte units per image to zero (all the same)
     int hints = 0; // CLUMPY_CUDA_HINTS (A/B): bit 2 = counter reads evict-first, bit 3 = zeroing stores evict-first
     float depth[3] = {0.f, 0.f, 0.f};
 };
