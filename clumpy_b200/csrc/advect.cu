@@ -713,6 +713,7 @@ static int advect_group(clumpy_advect* a, uint32_t nf, RecordSink* sink = nullpt
                 ca.frame_out[f] = slot[f] >= 0 ? a->imgs[slot[f]] : nullptr;
             }
             const int prev = (set + NSETS - 1) % NSETS;
+            ca.alone = !overlap; // (beside the next group's advect launch otherwise)
             ca.nzero = a->set_used[prev];
             for (int z = 0; z < ca.nzero; ++z) {
                 ca.zero[z] = reinterpret_cast<uint4*>(a->hist_buf[prev * a->fuse + z]);
@@ -1248,6 +1249,7 @@ static int route_back(clumpy_advect* adv, const RouteBack& b, bool overlap, Reco
             ca.cells[f] = reinterpret_cast<const char*>(route_band(adv, set, (int)f)) + row_off;
             ca.frame_out[f] = slot[f] >= 0 ? adv->imgs[slot[f]] + (size_t)y0 * adv->width : nullptr;
         }
+        ca.alone = !overlap; // (beside the next group's route launch otherwise)
         ca.nzero = rt.set_used[prev];
         for (int zf = 0; zf < ca.nzero; ++zf) {
             ca.zero[zf] = reinterpret_cast<uint4*>(route_band(adv, prev, zf));

@@ -344,9 +344,12 @@ int launch_composite_group(clumpy_cuda_ctx* ctx, cudaStream_t stream, const Grou
     int grid = std::min(ctx->sm_count, (int)ceil_div((uint32_t)a.ntiles, (uint32_t)threads / 32));
     if (a.nzero > 0) grid = ctx->sm_count;
     using Kern = void (*)(GroupCompositeArgs, const uint8_t*, uint32_t);
-    // CLUMPY_CUDA_COMPOSITE_PREFETCH=0|1 (A/B); 1024 threads leave 64 registers each: no room to look ahead
-    const int prefetch_env = [] { const char* v = getenv("CLUMPY_CUDA_COMPOSITE_PREFETCH"); return v ? atoi(v) : 1; }();
-    const bool prefetch = prefetch_env != 0 && t.kernel_size == 3 && threads == 512;
+    // The look-ahead variant takes all 128 registers of its 512 threads.  Beside a route launch on the other stream
+    // (multi-GPU) that costs more than it gives -- no route CTA fits next to it: 0.0198 against 0.0183 ms per frame
+    // on two ranks with a quarter of C4 -- so it is for launches that have the GPU to themselves.
+    // CLUMPY_CUDA_COMPOSITE_PREFETCH=0|1 forces it off / on (A/B); 1024 threads leave 64 registers each: no room.
+    const int prefetch_env = [] { const char* v = getenv("CLUMPY_CUDA_COMPOSITE_PREFETCH"); return v ? atoi(v) : -1; }();
+    const bool prefetch = (prefetch_env < 0 ? a.alone : prefetch_env != 0) && t.kernel_size == 3 && threads == 512;
     const Kern kern = t.kernel_size == 1 ? (threads == 256 ? composite_group_kernel<1, 256, false> : threads == 1024 ? composite_group_kernel<1, 1024, false> : composite_group_kernel<1, 512, false>)
                     : prefetch           ? composite_group_kernel<3, 512, true>
                                          : (threads == 256 ? composite_group_kernel<3, 256, false> : threads == 1024 ? composite_group_kernel<3, 1024, false> : composite_group_kernel<3, 512, false>);

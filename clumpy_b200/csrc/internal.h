@@ -161,6 +161,7 @@ struct GroupCompositeArgs {
     int nsrc = 0;
     uint32_t* errors = nullptr;
     unsigned long long timeout_ns = 0;
+    bool alone = true;           // no other launch shares the SMs with this one: take the whole register file (prefetch)
     // filled in by the launcher
     int tiles_x = 0, ntiles = 0, vec_ok = 0;
     uint32_t zero_units = 0;     // 16-byte units per image to zero (all the same)
