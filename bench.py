@@ -57,9 +57,10 @@ ALGO_BYTES_PER_POINT_STEP = 28  # 8 R + 8 W position, 8 R velocity 
 ALGO_BYTES_PER_PIXEL_FRAME = 2  # u8 framebuffer read + write
 PARITY_BAR = 0.999              # BASELINE.json: u8 frames within 1 LSB on >= 99.9 % of the pixels
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (8 frames, C4, steady state) from the round-2
-# `ncu --set full` capture of the two kernels (profiles/r2_ncu_steady_summary.txt: 1.269 + 0.747 GB and
-# 0.572 + 0.569 GB).  Constants, not measured by this script: a number taken under a profiler is never a bench value.
-NCU_TRAFFIC_BYTES = {"advect_fused_kernel": 2_016_050_000, "composite_group_kernel": 1_140_557_000}
+# `ncu --set full` captures of the two kernels (profiles/r2_ncu_steady_summary.txt: 1.269 + 0.747 GB;
+# profiles/r2_ncu_composite_lookahead_summary.txt: 0.573 + 0.528 GB).  Constants, not measured by this script: a
+# number taken under a profiler is never a bench value.
+NCU_TRAFFIC_BYTES = {"advect_fused_kernel": 2_016_050_000, "composite_group_kernel": 1_100_655_000}
 C3 = dict(width=16384, height=16384, octaves=[(1.0, 8.0, 0), (0.5, 16.0, 1), (0.25, 32.0, 2), (0.125, 64.0, 3)])
 C3_WORKLOAD = "C3: generate_simplex 16384x16384, 4 octaves (amp, freq, seed) = (1,8,0) (0.5,16,1) (0.25,32,2) (0.125,64,3) summed in FP32 in that order, then curl_2d; rows sharded across the GPUs"
 
