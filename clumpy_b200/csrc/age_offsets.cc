@@ -134,7 +134,8 @@ void mt_checkpoints_prefetch() {
 
 const uint32_t* mt_checkpoints() {
     mt_checkpoints_prefetch();
-    return ckpt_future.get().data();
+    const std::shared_future<std::vector<uint32_t>> mine = ckpt_future; // (each caller waits through its own copy)
+    return mine.get().data(); // the vector lives in the shared state, i.e. as long as ckpt_future does
 }
 
 } // namespace clumpy
