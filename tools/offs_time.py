@@ -1,3 +1,6 @@
+#!/usr/bin/env python3
+"""Times clumpy_cuda_age_offsets_dev (the reset offsets of advect_points.cc:127-135 drawn on the device) for the C4
+point count and for one eighth of it: CUDA events around the two launches."""
 import sys, os
 sys.path.insert(0, os.getcwd())
 import torch, clumpy_b200

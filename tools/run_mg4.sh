@@ -1,3 +1,5 @@
+#!/bin/bash
+# bench.py at N = 2 and N = 4 on a 4-GPU box (through gpurun --gpus 4): the 2000-step lines and the 2-GPU 20-step line.
 run() { # N K port
   python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $3 bench.py --gpus $1 --steps $2 --warmup 5 > gpurun_out/bench_mg$1_$2.json 2> gpurun_out/bench_mg$1_$2.err
   python -c "
