@@ -149,14 +149,21 @@ __global__ void __launch_bounds__(SIMPLEX_THREADS)
 simplex_octaves_kernel(const OctavePerms perms_arg, const OctaveArgs oa, uint32_t width, uint32_t row0, uint32_t nrows,
                        float* __restrict__ out, uint32_t* __restrict__ minmax, int vec_ok) {
     __shared__ uint8_t perm[SIMPLEX_MAX_OCTAVES][256];
+    // The per-octave step and scale go to shared memory too: indexed by the loop variable straight out of the
+    // kernel parameters they became a chain of 16 compare + predicated constant loads per pixel and octave (a quarter
+    // of the kernel's instructions, round 2 SASS).
+    __shared__ float oct_step[SIMPLEX_MAX_OCTAVES], oct_scale[SIMPLEX_MAX_OCTAVES];
     for (int o = 0; o < oa.n; ++o) perm[o][threadIdx.x] = perms_arg.p[o][threadIdx.x]; // blockDim.x == 256
+    if (threadIdx.x < SIMPLEX_MAX_OCTAVES) { oct_step[threadIdx.x] = oa.step[threadIdx.x]; oct_scale[threadIdx.x] = oa.scale[threadIdx.x]; }
     __syncthreads();
+    const int noct = oa.n;
     simplex_rows(width, nrows, out, minmax, vec_ok, [&](uint32_t col, uint32_t row) {
         float total = 0.f;
-        for (int o = 0; o < oa.n; ++o) {
-            const float uf = __fmul_rn(oa.step[o], (float)col);
-            const float vf = __fmul_rn(oa.step[o], (float)(row0 + row));
-            const float s = simplex2(perm[o], uf, vf) * oa.scale[o];
+        for (int o = 0; o < noct; ++o) {
+            const float step = oct_step[o];
+            const float uf = __fmul_rn(step, (float)col);
+            const float vf = __fmul_rn(step, (float)(row0 + row));
+            const float s = simplex2(perm[o], uf, vf) * oct_scale[o];
             total = o == 0 ? s : __fadd_rn(total, s);
         }
         return total;
