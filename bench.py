@@ -338,6 +338,11 @@ def run_ours(args):
     roof = roofline_block(n, w, h, ms / K, (adv_ms, comp_ms), (adv_alone, comp_alone), nf, hbm_peak, peak_src, atomic_gups)
     roof["steady_frac"] = roof["frac"] * (ms / K) / steady_ms
 
+    # The clock sampler stops here: it covers the device-timed regions above.  The e2e leg below is host wall clock,
+    # and an nvidia-smi query every 50 ms takes driver locks that its allocations and launches also want (one run in
+    # six measured 183 ms instead of 15.6 with the sampler still polling).
+    clocks = sampler.stop()
+
     # ---- e2e: whole command through the C ABI with host buffers ---------------------------------
     nrec = max(1, K // 2)
     ctx.advect_points(pts.numpy(), vel.numpy(), cfg["step_size"], cfg["kernel_size"], cfg["decay"], 2,
@@ -352,7 +357,6 @@ def run_ours(args):
     e2e_value = n * e2e_steps / dt
     h2d = (n * 8 + w * h * 8) / e2e_steps  # points + field (the reset offsets are drawn on the device)
     d2h = (nrec * w * h) / e2e_steps
-    clocks = sampler.stop()
 
     # ---- CPU baseline + parity at full size: the reference on the same inputs, 2 recorded frames ----
     cpu, parity = None, None
@@ -484,6 +488,8 @@ def run_multi(args):
     atomic_gups = n / (atomic_ms * 1e-3) / 1e9
     run.close()
 
+    clocks = sampler.stop() if sampler else None  # (the device-timed regions are over; see run_ours)
+
     # ---- e2e: host buffers in, this rank's band of every recorded frame out ------------------------
     nrec = max(1, K // 2)
     y0, y1 = mg.field_rows(h, world, rank)  # (an upper bound of the band height for the pinned buffer)
@@ -532,7 +538,6 @@ def run_multi(args):
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     dt = float(dt.item())
     note(f"e2e done: {dt:.3f} s")
-    clocks = sampler.stop() if sampler else None
     if rank == 0:
         e2e_steps = 2 * nrec
         roof = roofline_block(n, w, h, ms / K, None, None, nf, hbm_peak, peak_src, atomic_gups, world=world)
